@@ -1,0 +1,209 @@
+/*
+ * lmc_b200.h -- C ABI of the B200-native HMC / NUTS hot path (drop-in for eigenfoo/littlemcmc's sampler core).
+ *
+ * The reference (pure Python, /root/reference/littlemcmc) has no FFI; each entry point below replaces the
+ * Python call named in its comment (file:line in the reference tree).  A binding is a ctypes stub: see
+ * INTEGRATION.md.  Conventions:
+ *   - every pointer is a DEVICE pointer unless the comment says "host"; the library allocates nothing
+ *     persistent: all buffers (including scratch) are owned by the caller (PyTorch tensors in our host layer);
+ *   - per-chain vectors are rows of row-major [n_chains, ld] float64 arrays, `ld` even and >= ndim, row base
+ *     16-byte aligned (so rows can be moved with 128-bit accesses); elements [ndim, ld) are padding;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream) and
+ *     returns without synchronising;
+ *   - return value: LMC_OK or a negative LMC_ERR_*; no C++ exception crosses the boundary.  Numerical
+ *     failures are per-chain data, not errors: `diverging` statistics and the `status` bit mask
+ *     (the analogue of DivergenceInfo / ValueError("Bad initial energy"), base_hmc.py:145-148,164-179);
+ *   - re-entrant, no global state: RNG state is explicit (a per-chain 64-bit Philox key + counters derived
+ *     from the chain's transition index), unlike the reference's process-global numpy.random.seed stream.
+ */
+#ifndef LMC_B200_H
+#define LMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LMC_ABI_VERSION 1
+
+#define LMC_OK 0
+#define LMC_ERR_BADARG (-1)      /* null pointer, bad size/stride/alignment */
+#define LMC_ERR_UNSUPPORTED (-2) /* ndim / depth outside what the kernels are instantiated for */
+#define LMC_ERR_LAUNCH (-3)      /* cudaGetLastError() != cudaSuccess after the launch */
+#define LMC_ERR_WORKSPACE (-4)   /* workspace_bytes too small */
+
+/* ---- built-in target densities (the "user callback" evaluated inside the kernel) ---------------------- */
+#define LMC_TARGET_DIAG_GAUSSIAN 0 /* logp = -1/2 sum tau_i q_i^2 ; g = -(tau*q) ; logp = 0.5 * q.g          */
+#define LMC_TARGET_FUNNEL 1        /* Neal's funnel: q0=v~N(0,s^2), q_i|v~N(0,e^v)     */
+
+typedef struct lmc_target {
+  int32_t kind;      /* LMC_TARGET_*                                                                      */
+  int32_t reserved;
+  const double* tau; /* DIAG_GAUSSIAN: [ld] precisions 1/sigma^2 shared by all chains (padding = 0)       */
+  double v_scale;    /* FUNNEL: s (3.0 in cfg4)                                                           */
+} lmc_target;
+
+/* ---- randomness -------------------------------------------------------------------------------------- */
+#define LMC_RNG_TAPE 0   /* read pre-drawn numbers (parity tests: same numbers are fed to the CPU oracle)  */
+#define LMC_RNG_PHILOX 1 /* counter-based Philox4x32-10 inside the kernel, keyed per chain                 */
+
+typedef struct lmc_rng {
+  int32_t mode; /* LMC_RNG_*                                                                              */
+  int32_t reserved;
+  /* TAPE: standard normals for the momentum draw (quadpotential.py:221-224), one row per transition of
+   * this call: normals[(chain * n_trans + t) * ndim + i]                                                 */
+  const double* normals;
+  /* TAPE: uniforms in [0,1) consumed by sequential counter, reset every transition, in the reference's
+   * order (math.py:25 via nuts.py:213,404,321; hmc.py:141,166): uniforms[(chain * n_trans + t) * u_stride + k] */
+  const double* uniforms;
+  int64_t u_stride;
+  const uint64_t* seeds; /* PHILOX: [n_chains] keys (the per-chain seeds of sampling.py:131-134)           */
+} lmc_rng;
+
+/* ---- per-chain adaptation scalars: adapt[chain * LMC_ADAPT_STRIDE + k] ------------------------------- */
+#define LMC_ADAPT_LOG_STEP 0  /* DualAverageAdaptation._log_step   (step_sizes.py:51)                      */
+#define LMC_ADAPT_LOG_BAR 1   /* ._log_bar                                                                 */
+#define LMC_ADAPT_HBAR 2      /* ._hbar                                                                    */
+#define LMC_ADAPT_COUNT 3     /* ._count                                                                   */
+#define LMC_ADAPT_MU 4        /* ._mu = log(10 * initial_step)                                             */
+#define LMC_ADAPT_W_FG 5      /* QuadPotentialDiagAdapt._foreground_var.w_sum (quadpotential.py:305)       */
+#define LMC_ADAPT_W_BG 6      /* ._background_var.w_sum                                                    */
+#define LMC_ADAPT_NSAMPLES 7  /* ._n_samples                                                               */
+#define LMC_ADAPT_WINDOW 8    /* .adaptation_window                                                        */
+#define LMC_ADAPT_STRIDE 10
+
+/* ---- per-transition statistics: stats[(chain * n_trans + t) * LMC_NSTATS + k], all float64 ------------ */
+#define LMC_NSTATS 12
+/* NUTS (nuts.py:87-101, 427-435)                 HMC (hmc.py:36-50, 173-181)                              */
+#define LMC_STAT_DEPTH 0           /* depth            | n_steps                                           */
+#define LMC_STAT_TREE_SIZE 1       /* tree_size        | path_length                                       */
+#define LMC_STAT_ACCEPT 2          /* mean_tree_accept | accept                                            */
+#define LMC_STAT_ENERGY 3          /* energy                                                               */
+#define LMC_STAT_ENERGY_ERROR 4    /* energy_error                                                         */
+#define LMC_STAT_MAX_ENERGY_ERROR 5/* max_energy_error | accepted                                          */
+#define LMC_STAT_MODEL_LOGP 6      /* model_logp                                                           */
+#define LMC_STAT_DIVERGING 7       /* diverging                                                            */
+#define LMC_STAT_TUNE 8            /* tune                                                                 */
+#define LMC_STAT_STEP_SIZE 9       /* step_size  (post-update: the NEXT draw's, base_hmc.py:161,188)       */
+#define LMC_STAT_STEP_SIZE_BAR 10  /* step_size_bar                                                        */
+#define LMC_STAT_N_UNIFORMS 11     /* uniforms consumed by this transition (bookkeeping, not in reference) */
+
+/* ---- status bits: status[chain] ------------------------------------------------------------------------ */
+#define LMC_STATUS_BAD_INITIAL_ENERGY 1 /* non-finite start energy: the reference raises ValueError
+                                           (base_hmc.py:145-148); the chain stops and its remaining
+                                           trace/stats rows are NaN                                         */
+#define LMC_STATUS_TAPE_EXHAUSTED 2     /* TAPE mode ran past u_stride                                      */
+
+/*
+ * Arguments of one sampling call: `n_trans` consecutive transitions of every chain, i.e. the loop body of
+ * sampling._iter_sample (sampling.py:507-513) around BaseHMC._astep (base_hmc.py:140-190), for all chains.
+ */
+typedef struct lmc_sampler_args {
+  int32_t abi_version; /* LMC_ABI_VERSION                                                                  */
+  int32_t n_chains;
+  int32_t ndim;        /* model_ndim                                                                        */
+  int32_t reserved0;
+  int64_t ld;          /* row stride (elements) of every [n_chains, ld] array below                         */
+  lmc_target target;
+
+  /* chain state, updated in place */
+  double* q;           /* [n_chains, ld] current position (`q0` of _astep, replaced by `hmc_step.end.q`)    */
+  double* var;         /* [n_chains, ld] QuadPotentialDiag(Adapt)._var / .v: diagonal of the inverse mass   */
+
+  /* adaptation (potential.update: quadpotential.py:231-245; step_adapt.update: step_sizes.py:71-92) */
+  int32_t adapt_mass;  /* 1: QuadPotentialDiagAdapt, 0: static QuadPotentialDiag                            */
+  int32_t adapt_step_size; /* BaseHMC.adapt_step_size                                                       */
+  double* mean_fg;     /* [n_chains, ld] _foreground_var.mean       (NULL allowed if !adapt_mass)           */
+  double* rawvar_fg;   /* [n_chains, ld] _foreground_var.raw_var                                            */
+  double* mean_bg;     /* [n_chains, ld] _background_var.mean                                               */
+  double* rawvar_bg;   /* [n_chains, ld] _background_var.raw_var                                            */
+  double* adapt;       /* [n_chains, LMC_ADAPT_STRIDE]                                                      */
+  double window_multiplier; /* adaptation_window_multiplier                                                 */
+  double target_accept, gamma, k, t0; /* DualAverageAdaptation parameters                                   */
+
+  /* schedule */
+  int64_t iter0;       /* iter_count of the first transition of this call (0 at the start of a run)         */
+  int64_t n_tune;      /* transitions with iter_count < n_tune are tuning (sampling.py:503,510-511)          */
+  int32_t n_trans;     /* transitions to run in this call                                                   */
+  int32_t reserved1;
+
+  /* step-method parameters (nuts.py:103-121, hmc.py:52-69) */
+  double Emax;
+  int32_t max_treedepth;       /* NUTS */
+  int32_t early_max_treedepth; /* NUTS: cap while tune && iter_count < 200 (nuts.py:205-208)                */
+  double path_length;          /* HMC  */
+  int32_t max_steps;           /* HMC  */
+  int32_t reserved2;
+
+  lmc_rng rng;
+
+  /* outputs */
+  double* trace;       /* trace[chain * trace_chain_stride + t * trace_draw_stride + i], i < ndim           */
+  int64_t trace_chain_stride;
+  int64_t trace_draw_stride;
+  double* stats;       /* [n_chains, n_trans, LMC_NSTATS]                                                   */
+  int32_t* status;     /* [n_chains] OR-ed LMC_STATUS_* bits                                                */
+
+  /* scratch and launch control */
+  void* workspace;     /* >= lmc_workspace_bytes(...) bytes, 16-byte aligned                                */
+  int64_t workspace_bytes;
+  void* stream;        /* cudaStream_t                                                                      */
+  int32_t tune_group;  /* 0 = library picks threads-per-chain; else force 32/64/128/256/512 (experiments)   */
+  int32_t tune_smem_vecs; /* -1 = library picks how many scratch vectors live in shared memory; else force  */
+  int32_t tune_max_slots; /* 0 = library picks the number of resident chain slots; else cap it              */
+  int32_t reserved3;
+} lmc_sampler_args;
+
+/* Library / ABI version (LMC_ABI_VERSION of the build). */
+int lmc_abi_version(void);
+
+/* Bytes of scratch lmc_nuts_sample / lmc_hmc_sample need for this problem (host call, no GPU work).
+ * `kind`: 0 = NUTS, 1 = HMC; `tune_group` as in lmc_sampler_args.  Returns < 0 on unsupported sizes. */
+int64_t lmc_workspace_bytes(int32_t kind, int32_t n_chains, int32_t ndim, int32_t max_treedepth,
+                            int32_t tune_group);
+
+/* n_trans NUTS transitions for all chains: replaces NUTS._astep -> NUTS._hamiltonian_step -> _Tree.extend /
+ * _build_subtree / _single_step (nuts.py:204-224, 284-417) with CpuLeapfrogIntegrator.step
+ * (integration.py:100-121), QuadPotentialDiag(Adapt).velocity/energy/random/update
+ * (quadpotential.py:206-245, 367-387) and DualAverageAdaptation.current/update (step_sizes.py:58-92). */
+int lmc_nuts_sample(const lmc_sampler_args* args);
+
+/* Same for HamiltonianMC._astep -> _hamiltonian_step (hmc.py:140-182). */
+int lmc_hmc_sample(const lmc_sampler_args* args);
+
+/* CpuLeapfrogIntegrator.compute_state (integration.py:52-66) for all chains with a built-in target:
+ * g = dlogp(q), v = var*p, energy = 0.5 p.v - logp.  var_stride = ld for per-chain var, 0 to broadcast one row. */
+int lmc_compute_state(const lmc_target* target, int32_t n_chains, int32_t ndim, int64_t ld, const double* q,
+                      const double* p, const double* var, int64_t var_stride, double* v, double* g,
+                      double* energy, double* logp, void* stream);
+
+/* CpuLeapfrogIntegrator.step (integration.py:100-121) for all chains with a built-in target; eps[chain] may be
+ * negative.  In-place (q_out == q etc.) is allowed. */
+int lmc_leapfrog_step(const lmc_target* target, int32_t n_chains, int32_t ndim, int64_t ld, const double* eps,
+                      const double* q, const double* p, const double* g, const double* var, int64_t var_stride,
+                      double* q_out, double* p_out, double* v_out, double* g_out, double* energy, double* logp,
+                      void* stream);
+
+/* The two halves of integration.py:100-121 around an external (torch) gradient evaluation:
+ *   half1: p <- p + eps/2 * g ; q <- q + eps * (var*p)                          (lines 105-112)
+ *   half2: p <- p + eps/2 * g_new ; v = var*p ; energy = 0.5 p.v - logp[chain]  (lines 116-119)
+ * `active` (nullable) masks chains: rows with active[chain]==0 are left untouched. */
+int lmc_leapfrog_half1(int32_t n_chains, int32_t ndim, int64_t ld, const double* eps, const int32_t* active,
+                       double* q, double* p, const double* g, const double* var, int64_t var_stride, void* stream);
+int lmc_leapfrog_half2(int32_t n_chains, int32_t ndim, int64_t ld, const double* eps, const int32_t* active,
+                       double* p, double* v, const double* g_new, const double* logp, const double* var,
+                       int64_t var_stride, double* energy, void* stream);
+
+/* Dump the numbers the PHILOX mode would consume into tapes (tests: Philox path == tape path == oracle).
+ * normals: [n_chains, n_trans, ndim]; uniforms: [n_chains, n_trans, u_stride]. */
+int lmc_rng_fill(const uint64_t* seeds, int32_t n_chains, int32_t ndim, int64_t iter0, int32_t n_trans,
+                 int64_t u_stride, double* normals, double* uniforms, void* stream);
+
+/* Last CUDA error string seen by the library on this thread (host pointer, static storage). */
+const char* lmc_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LMC_B200_H */

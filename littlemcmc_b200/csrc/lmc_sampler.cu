@@ -1,0 +1,80 @@
+// Entry points lmc_nuts_sample / lmc_hmc_sample / lmc_workspace_bytes: argument validation and dispatch to the
+// per-(target, kind) instantiations of the sampler kernel (lmc_sampler.cuh, lmc_inst_*.cu).
+#include "lmc_sampler.cuh"
+
+namespace lmc {
+
+static int check_args(const lmc_sampler_args* a, int kind) {
+  if (!a) return LMC_ERR_BADARG;
+  if (a->abi_version != LMC_ABI_VERSION) return LMC_ERR_BADARG;
+  if (a->n_chains < 0 || a->ndim < 1 || a->n_trans < 0) return LMC_ERR_BADARG;
+  if (a->ld < a->ndim || (a->ld & 1)) return LMC_ERR_BADARG;
+  if (!a->q || !a->var || !a->adapt || !a->trace || !a->stats || !a->status) return LMC_ERR_BADARG;
+  if (((uintptr_t)a->q | (uintptr_t)a->var | (uintptr_t)a->workspace) & 15) return LMC_ERR_BADARG;
+  if (a->adapt_mass) {
+    if (!a->mean_fg || !a->rawvar_fg || !a->mean_bg || !a->rawvar_bg) return LMC_ERR_BADARG;
+    if (((uintptr_t)a->mean_fg | (uintptr_t)a->rawvar_fg | (uintptr_t)a->mean_bg | (uintptr_t)a->rawvar_bg) & 15)
+      return LMC_ERR_BADARG;
+  }
+  if (a->rng.mode == LMC_RNG_TAPE) {
+    if (!a->rng.normals || !a->rng.uniforms || a->rng.u_stride < 1) return LMC_ERR_BADARG;
+  } else if (a->rng.mode == LMC_RNG_PHILOX) {
+    if (!a->rng.seeds) return LMC_ERR_BADARG;
+  } else {
+    return LMC_ERR_BADARG;
+  }
+  if (kind == KIND_NUTS) {
+    if (a->max_treedepth < 1 || a->max_treedepth > kMaxDepth) return LMC_ERR_UNSUPPORTED;
+    if (a->early_max_treedepth < 0 || a->early_max_treedepth > kMaxDepth) return LMC_ERR_UNSUPPORTED;
+    if (!a->workspace) return LMC_ERR_BADARG;
+  } else {
+    if (a->max_steps < 1) return LMC_ERR_BADARG;
+  }
+  if (a->target.kind == LMC_TARGET_DIAG_GAUSSIAN) {
+    if (!a->target.tau || ((uintptr_t)a->target.tau & 15)) return LMC_ERR_BADARG;
+  } else if (a->target.kind != LMC_TARGET_FUNNEL) {
+    return LMC_ERR_UNSUPPORTED;
+  }
+  return LMC_OK;
+}
+
+// one translation unit per (target, kind): lmc_inst_*.cu
+int run_gauss_nuts(const lmc_sampler_args& a, const DiagGaussian& t);
+int run_gauss_hmc(const lmc_sampler_args& a, const DiagGaussian& t);
+int run_funnel_nuts(const lmc_sampler_args& a, const Funnel& t);
+int run_funnel_hmc(const lmc_sampler_args& a, const Funnel& t);
+
+static int sample_entry(const lmc_sampler_args* a, int kind) {
+  const int rc = check_args(a, kind);
+  if (rc != LMC_OK) return rc;
+  if (a->n_chains == 0 || a->n_trans == 0) return LMC_OK;
+  if (a->target.kind == LMC_TARGET_DIAG_GAUSSIAN) {
+    DiagGaussian t{reinterpret_cast<const double2*>(a->target.tau)};
+    return kind == KIND_NUTS ? run_gauss_nuts(*a, t) : run_gauss_hmc(*a, t);
+  }
+  Funnel t{1.0 / (a->target.v_scale * a->target.v_scale), 0.5 * (double)(a->ndim - 1)};
+  return kind == KIND_NUTS ? run_funnel_nuts(*a, t) : run_funnel_hmc(*a, t);
+}
+
+}  // namespace lmc
+
+extern "C" int64_t lmc_workspace_bytes(int32_t kind, int32_t n_chains, int32_t ndim, int32_t max_treedepth,
+                                       int32_t tune_group) {
+  if (kind == lmc::KIND_HMC) return 16;
+  if (kind != lmc::KIND_NUTS || max_treedepth < 1 || max_treedepth > lmc::kMaxDepth) return LMC_ERR_UNSUPPORTED;
+  lmc::Shape s;
+  if (!lmc::pick_shape(ndim, tune_group, &s)) return LMC_ERR_UNSUPPORTED;
+  // resident groups are bounded by 2048 threads per SM and by the number of chains
+  int dev = 0, n_sm = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  (void)cudaGetLastError();
+  const int cpb = s.G >= 64 ? 1 : 128 / s.G;
+  long long slots = (long long)n_sm * (2048 / s.G);
+  const long long by_chains = (((long long)n_chains + cpb - 1) / cpb) * cpb;
+  if (slots > by_chains) slots = by_chains;
+  if (slots < cpb) slots = cpb;
+  return slots * lmc::ws_vecs_nuts(max_treedepth) * (long long)(s.G * s.NP) * (long long)sizeof(double2);
+}
+
+extern "C" int lmc_nuts_sample(const lmc_sampler_args* args) { return lmc::sample_entry(args, lmc::KIND_NUTS); }
+extern "C" int lmc_hmc_sample(const lmc_sampler_args* args) { return lmc::sample_entry(args, lmc::KIND_HMC); }

@@ -1,0 +1,183 @@
+"""Device-side chain state and kernel launches (host plumbing over the C ABI; PyTorch tensors own the memory).
+
+One `DeviceChains` holds everything the reference keeps per chain in Python objects -- the current position,
+`QuadPotentialDiag(Adapt)`'s arrays and `DualAverageAdaptation`'s scalars -- as row-major [n_chains, ld] / [n_chains, k]
+float64 tensors ("each becomes a [C, D] (or [C]) row-major device tensor").
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def padded_ld(ndim):
+    return int(ndim) + (int(ndim) & 1)
+
+
+def as_device_rows(x, n_chains, ndim, device):
+    """numpy/torch [D] or [C, D] -> float64 device tensor [C, ld] with zero padding."""
+    t = torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x, dtype=torch.float64, device=device)
+    if t.ndim == 1:
+        t = t.unsqueeze(0).expand(n_chains, -1)
+    if t.shape != (n_chains, ndim):
+        raise ValueError("expected shape (%d, %d) or (%d,), got %s" % (n_chains, ndim, ndim, tuple(t.shape)))
+    out = torch.zeros(n_chains, padded_ld(ndim), dtype=torch.float64, device=device)
+    out[:, :ndim] = t
+    return out
+
+
+class DeviceChains:
+    """State of `n_chains` independent chains on one GPU."""
+
+    def __init__(self, n_chains, ndim, device):
+        L.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise L.LmcError("littlemcmc_b200 runs on CUDA devices only (got %s); there is no CPU fallback" % device)
+        self.n_chains, self.ndim, self.ld = int(n_chains), int(ndim), padded_ld(ndim)
+        z = lambda *s: torch.zeros(*s, dtype=torch.float64, device=self.device)  # noqa: E731
+        self.q = z(self.n_chains, self.ld)
+        self.var = z(self.n_chains, self.ld)
+        self.mean_fg, self.rawvar_fg = z(self.n_chains, self.ld), z(self.n_chains, self.ld)
+        self.mean_bg, self.rawvar_bg = z(self.n_chains, self.ld), z(self.n_chains, self.ld)
+        self.adapt = z(self.n_chains, L.ADAPT_STRIDE)
+        self.status = torch.zeros(self.n_chains, dtype=torch.int32, device=self.device)
+        self._workspace = None
+
+    # -- initialisation from the host-side descriptors (reference reset(): quadpotential.py:195-204, step_sizes.py:49-56)
+    def reset_potential(self, var, mean, weight, window):
+        C_, D = self.n_chains, self.ndim
+        self.var.copy_(as_device_rows(var, C_, D, self.device))
+        self.mean_fg.copy_(as_device_rows(mean, C_, D, self.device))
+        self.rawvar_fg.copy_(self.var * float(weight))          # raw_var[:] *= w_sum (quadpotential.py:315)
+        self.mean_bg.zero_()
+        self.rawvar_bg.zero_()
+        self.adapt[:, L.ADAPT_W_FG] = float(weight)
+        self.adapt[:, L.ADAPT_W_BG] = 0.0
+        self.adapt[:, L.ADAPT_NSAMPLES] = 0.0
+        self.adapt[:, L.ADAPT_WINDOW] = float(window)
+
+    def reset_step_adapt(self, initial_step):
+        ls = float(np.log(initial_step))
+        self.adapt[:, L.ADAPT_LOG_STEP] = ls
+        self.adapt[:, L.ADAPT_LOG_BAR] = ls
+        self.adapt[:, L.ADAPT_HBAR] = 0.0
+        self.adapt[:, L.ADAPT_COUNT] = 1.0
+        self.adapt[:, L.ADAPT_MU] = float(np.log(10 * initial_step))
+
+    def set_position(self, q):
+        self.q.copy_(as_device_rows(q, self.n_chains, self.ndim, self.device))
+
+    def workspace(self, nbytes):
+        if self._workspace is None or self._workspace.numel() < nbytes:
+            self._workspace = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return self._workspace
+
+
+class FusedTarget:
+    """A built-in target density evaluated inside the kernels (include/lmc_b200.h: lmc_target)."""
+
+    def __init__(self, kind, ndim, tau=None, v_scale=3.0):
+        self.kind, self.ndim, self.v_scale = int(kind), int(ndim), float(v_scale)
+        self.tau_host = None if tau is None else np.ascontiguousarray(tau, dtype=np.float64)
+        self._tau_dev = {}
+
+    def c_struct(self, device):
+        t = L.Target()
+        t.kind, t.v_scale = self.kind, self.v_scale
+        if self.kind == L.TARGET_DIAG_GAUSSIAN:
+            key = str(device)
+            if key not in self._tau_dev:
+                buf = torch.zeros(padded_ld(self.ndim), dtype=torch.float64, device=device)
+                buf[: self.ndim] = torch.as_tensor(self.tau_host, device=device)
+                self._tau_dev[key] = buf
+            t.tau = self._tau_dev[key].data_ptr()
+        return t
+
+
+def run_transitions(kind, chains, target, *, n_trans, iter0, n_tune, params, seeds=None, tapes=None,
+                    trace=None, stats=None, knobs=None, stream=None):
+    """Enqueue `n_trans` transitions of every chain (lmc_nuts_sample / lmc_hmc_sample).  Returns (trace, stats)
+    device tensors [C, n_trans, D] and [C, n_trans, NSTATS].  Asynchronous on the current CUDA stream."""
+    lib = L.load()
+    dev = chains.device
+    Cn, D = chains.n_chains, chains.ndim
+    if trace is None:
+        trace = torch.empty(Cn, n_trans, D, dtype=torch.float64, device=dev)
+    if stats is None:
+        stats = torch.empty(Cn, n_trans, L.NSTATS, dtype=torch.float64, device=dev)
+    assert trace.is_contiguous() or trace.stride(2) == 1
+    a = L.SamplerArgs()
+    a.abi_version, a.n_chains, a.ndim, a.ld = L.ABI_VERSION, Cn, D, chains.ld
+    a.target = target.c_struct(dev)
+    a.q, a.var = chains.q.data_ptr(), chains.var.data_ptr()
+    a.adapt_mass, a.adapt_step_size = int(params["adapt_mass"]), int(params["adapt_step_size"])
+    a.mean_fg, a.rawvar_fg = chains.mean_fg.data_ptr(), chains.rawvar_fg.data_ptr()
+    a.mean_bg, a.rawvar_bg = chains.mean_bg.data_ptr(), chains.rawvar_bg.data_ptr()
+    a.adapt = chains.adapt.data_ptr()
+    a.window_multiplier = float(params.get("window_multiplier", 1.0))
+    a.target_accept, a.gamma = float(params["target_accept"]), float(params["gamma"])
+    a.k, a.t0 = float(params["k"]), float(params["t0"])
+    a.iter0, a.n_tune, a.n_trans = int(iter0), int(n_tune), int(n_trans)
+    a.Emax = float(params["Emax"])
+    a.max_treedepth = int(params.get("max_treedepth", 10))
+    a.early_max_treedepth = int(params.get("early_max_treedepth", 8))
+    a.path_length, a.max_steps = float(params.get("path_length", 2.0)), int(params.get("max_steps", 1024))
+    keep = []
+    if tapes is not None:
+        normals, uniforms = tapes
+        normals = torch.as_tensor(normals, dtype=torch.float64, device=dev).contiguous()
+        uniforms = torch.as_tensor(uniforms, dtype=torch.float64, device=dev).contiguous()
+        assert normals.shape == (Cn, n_trans, D), normals.shape
+        assert uniforms.shape[:2] == (Cn, n_trans), uniforms.shape
+        a.rng.mode, a.rng.normals, a.rng.uniforms = L.RNG_TAPE, normals.data_ptr(), uniforms.data_ptr()
+        a.rng.u_stride = uniforms.shape[2]
+        keep += [normals, uniforms]
+    else:
+        if seeds is None:
+            raise ValueError("either per-chain seeds or tapes are required")
+        a.rng.mode, a.rng.seeds = L.RNG_PHILOX, seeds.data_ptr()
+        keep.append(seeds)
+    a.trace, a.trace_chain_stride, a.trace_draw_stride = trace.data_ptr(), trace.stride(0), trace.stride(1)
+    a.stats, a.status = stats.data_ptr(), chains.status.data_ptr()
+    knobs = knobs or {}
+    a.tune_group = int(knobs.get("group", 0))
+    a.tune_smem_vecs = int(knobs.get("smem_vecs", -1))
+    a.tune_max_slots = int(knobs.get("max_slots", 0))
+    with torch.cuda.device(dev):
+        nbytes = lib.lmc_workspace_bytes(kind, Cn, D, a.max_treedepth, a.tune_group)
+        if nbytes < 0:
+            L.check(int(nbytes), "lmc_workspace_bytes")
+        ws = chains.workspace(nbytes)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        a.stream = (stream or torch.cuda.current_stream(dev)).cuda_stream
+        fn = lib.lmc_nuts_sample if kind == L.KIND_NUTS else lib.lmc_hmc_sample
+        L.check(fn(C.byref(a)), "lmc_nuts_sample" if kind == L.KIND_NUTS else "lmc_hmc_sample")
+    for t in keep:  # tensors referenced by the enqueued kernel must outlive it on this stream
+        t.record_stream(torch.cuda.current_stream(dev)) if t.is_cuda else None
+    return trace, stats
+
+
+def rng_fill(seeds, ndim, iter0, n_trans, u_stride):
+    """The numbers PHILOX mode consumes, as tapes (lmc_rng_fill)."""
+    lib = L.load()
+    dev = seeds.device
+    Cn = seeds.shape[0]
+    normals = torch.empty(Cn, n_trans, ndim, dtype=torch.float64, device=dev)
+    uniforms = torch.empty(Cn, n_trans, u_stride, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        L.check(lib.lmc_rng_fill(_ptr(seeds), Cn, ndim, int(iter0), int(n_trans), int(u_stride), _ptr(normals),
+                                 _ptr(uniforms), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "lmc_rng_fill")
+    return normals, uniforms
+
+
+def seeds_tensor(seeds, device):
+    """Per-chain integer seeds -> uint64 keys on the device (stored as int64 bit patterns)."""
+    arr = np.asarray(seeds, dtype=np.uint64).astype(np.int64)
+    return torch.as_tensor(arr, device=device)
