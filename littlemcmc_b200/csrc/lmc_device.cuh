@@ -52,6 +52,43 @@ __device__ __forceinline__ double log1mexp(double x) {  // math.py:28-35
   return x < 0.683 ? log(-expm1(-x)) : log1p(-exp(-x));
 }
 
+// ---- extended-range positive reals for the tree weights -------------------------------------------------------------
+// The reference keeps subtree sizes in the log domain (log_size, log_weighted_accept_sum) and pays two logaddexp and
+// one log(u) per merge (nuts.py:400-404).  The same real numbers are kept here as value = m * 2^e with a double
+// mantissa and an int exponent: the range is unbounded for any Emax, a merge is two scaled additions and one
+// multiply-compare, and the only transcendental left is one exp per leaf.  Results agree with the log-domain ones to
+// a few ulp; a decision can only differ when u lies within ~1e-15 (relative) of its threshold.
+struct XF {
+  double m;  // >= 0
+  int e;
+};
+__device__ __forceinline__ XF xf_zero() { return XF{0.0, -(1 << 28)}; }
+__device__ __forceinline__ XF xf_one() { return XF{1.0, 0}; }
+// exp(x) for finite x of any magnitude: x = n ln2 + r, |r| <= ln2/2 (Cody-Waite, fdlibm's split of ln2)
+__device__ __forceinline__ XF xf_exp(double x) {
+  const double n = rint(x * 1.44269504088896338700e+00);
+  double r = fma(-n, 6.93147180369123816490e-01, x);
+  r = fma(-n, 1.90821492927058770002e-10, r);
+  return XF{exp(r), (int)n};
+}
+__device__ __forceinline__ double xf_scale(double m, int d) {  // m * 2^d, d <= 0, flushing to 0 far below
+  return d < -1000 ? 0.0 : m * __longlong_as_double((long long)(1023 + d) << 52);
+}
+__device__ __forceinline__ XF xf_add(XF a, XF b) {
+  const int e = a.e > b.e ? a.e : b.e;
+  return XF{xf_scale(a.m, a.e - e) + xf_scale(b.m, b.e - e), e};
+}
+__device__ __forceinline__ XF xf_sqr(XF a) { return XF{a.m * a.m, 2 * a.e}; }
+// u * a < b   (u in [0,1), a, b >= 0)
+__device__ __forceinline__ bool xf_u_less(double u, XF a, XF b) {
+  const int e = a.e > b.e ? a.e : b.e;
+  return u * xf_scale(a.m, a.e - e) < xf_scale(b.m, b.e - e);
+}
+__device__ __forceinline__ double xf_value(XF a) { return a.m == 0.0 ? 0.0 : scalbn(a.m, a.e); }
+__device__ __forceinline__ double xf_ratio(XF a, XF b) {  // a / b, b > 0
+  return a.m == 0.0 ? 0.0 : scalbn(a.m / b.m, a.e - b.e);
+}
+
 // ---- Philox4x32-10 (Salmon et al. 2011), written out so the stream is a documented function of
 //      (key = per-chain seed, transition index, counter) and can be dumped by lmc_rng_fill -------------------
 struct u32x4 { uint32_t x, y, z, w; };

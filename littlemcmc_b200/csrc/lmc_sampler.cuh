@@ -38,6 +38,16 @@ __host__ __device__ constexpr int vid_tail(int max_depth) { return max_depth < 1
 enum { T_LQ = 0, T_LP, T_LG, T_RQ, T_RP, T_RG, T_PSUM, T_PROPQ, T_COUNT };
 __host__ __device__ constexpr int ws_vecs_nuts(int max_depth) { return vid_tail(max_depth) + T_COUNT; }
 
+// per-level scalars of the subtree stack, one copy per chain in shared memory (written by lane 0 only; every read
+// is separated from the write by a group barrier / __syncwarp, see the push below)
+struct StackScalars {
+  double wm[kMaxDepth], am[kMaxDepth];   // mantissas of exp(log_size), exp(log_weighted_accept_sum)
+  double pE[kMaxDepth], plogp[kMaxDepth];  // proposal energy / model_logp
+  int we[kMaxDepth], ae[kMaxDepth];      // exponents
+  int pslot[kMaxDepth];                  // proposal slot
+  int pad[kMaxDepth];
+};
+
 struct KernelCfg {
   int n_smem_vecs;  // scratch vectors per group kept in shared memory
   int ws_vecs;      // scratch vectors per slot in the global workspace (ids are absolute: smem ids unused there)
@@ -75,6 +85,8 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
   double2* const sm = smem2 + (size_t)gib * cfg.n_smem_vecs * VS;
   double* const red = reinterpret_cast<double*>(smem2 + (size_t)CPB * cfg.n_smem_vecs * VS) +
                       gib * (2 * Group<G>::kWarps * kRedSlots);
+  StackScalars* const ss = reinterpret_cast<StackScalars*>(
+      reinterpret_cast<double*>(smem2 + (size_t)CPB * cfg.n_smem_vecs * VS) + CPB * (2 * Group<G>::kWarps * kRedSlots)) + gib;
   double2* const ws = reinterpret_cast<double2*>(a.workspace) + (size_t)slot * cfg.ws_vecs * VS;
   Group<G> grp(lane, red);
 
@@ -167,7 +179,9 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
         // ---- NUTS._hamiltonian_step + _Tree  (nuts.py:204-224, 251-435) -----------------------------------------
         const int max_depth = (tune && it < 200) ? a.early_max_treedepth : a.max_treedepth;  // nuts.py:205-208
         // trajectory state (nuts.py:267-282)
-        double ls = 0.0, lwas = -CUDART_INF, max_dE = 0.0;
+        XF Wp = xf_zero();  // exp(log_size) - 1: total weight of the accepted subtrees (the start point has weight 1)
+        XF Acc = xf_zero(); // exp(log_weighted_accept_sum)
+        double max_dE = 0.0;
         double prop_E = E0, prop_logp = logp0;
         int depth = 0;
         long long n_prop = 0;
@@ -184,12 +198,10 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
           vec(tail + T_PSUM)[k * G] = p[k];   // p_sum = start.p.copy()
           vec(tail + T_PROPQ)[k * G] = q[k];  // proposal = start
         }
-        // per-level scalars of the subtree stack
-        double st_ls[kMaxDepth], st_lw[kMaxDepth], st_pE[kMaxDepth], st_plogp[kMaxDepth];
-        int st_pslot[kMaxDepth];
-
         for (int d = 0; d < max_depth; ++d) {  // nuts.py:212
-          const int dir = (log(next_uniform()) < -0.693147180559945309417232121458176568) ? 1 : -1;  // :213
+          // logbern(log 0.5): log(u) < log(0.5) <=> u < 0.5 (log is monotone; the two can only disagree for the single
+          // double adjacent to 0.5)                                                                   nuts.py:213
+          const int dir = (next_uniform() < 0.5) ? 1 : -1;
           if (reg_edge != 0 && reg_edge != dir) {  // fetch the edge we extend from (nuts.py:297 / 306)
             const int base = tail + (dir > 0 ? T_RQ : T_LQ);
 #pragma unroll
@@ -205,7 +217,8 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
           long long n_leaves = 0;
           // summary of the subtree being assembled on top of the stack ("cur"); its right edge is always z
           double2 cur_lp[NP], cur_ps[NP];
-          double cur_ls = 0.0, cur_lw = 0.0, cur_pE = 0.0, cur_plogp = 0.0;
+          XF cur_w = xf_zero(), cur_a = xf_zero();  // exp(log_size), exp(log_weighted_accept_sum) of "cur"
+          double cur_pE = 0.0, cur_plogp = 0.0;
           int cur_pslot = kLeafProp;
 
           const unsigned n_leaf_total = 1u << d;
@@ -220,8 +233,8 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
               fail = 1;
               break;
             }
-            cur_ls = -dE;                    // log_size
-            cur_lw = -dE + fmin(0.0, -dE);   // log_p_accept_weighted (:363)
+            cur_w = xf_exp(-dE);                             // log_size = -dE
+            cur_a = (-dE < 0.0) ? xf_sqr(cur_w) : cur_w;     // log_p_accept_weighted = -dE + min(0, -dE)  (:363)
             cur_pE = E;
             cur_plogp = logp;
             cur_pslot = kLeafProp;
@@ -281,20 +294,20 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
               for (int k = 0; k < NP; ++k) cur_lp[k] = t1_lp[k];  // left edge of the merged tree
               const bool turn = (dots[0] <= 0) || (dots[1] <= 0) || (dots[2] <= 0) || (dots[3] <= 0) ||
                                 (dots[4] <= 0) || (dots[5] <= 0);  // :391-398 (dots 2..5 preset to 1 at level 0)
-              const double t1_ls = st_ls[lvl];
-              const double nls = logaddexp(t1_ls, cur_ls);        // :400
-              const double nlw = logaddexp(st_lw[lvl], cur_lw);   // :401-403
-              // logbern(tree2.log_size - log_size): the uniform is drawn even when turning (:404)
-              if (log(next_uniform()) < cur_ls - nls) {
-                free_slots |= 1u << st_pslot[lvl];  // keep tree2's proposal, drop tree1's
+              const XF nw = xf_add(XF{ss->wm[lvl], ss->we[lvl]}, cur_w);   // log_size = logaddexp(...)        (:400)
+              const XF na = xf_add(XF{ss->am[lvl], ss->ae[lvl]}, cur_a);   // log_weighted_accept_sum      (:401-403)
+              // logbern(tree2.log_size - log_size) <=> u * size < size2; the uniform is drawn even when turning (:404)
+              const int t1_pslot = ss->pslot[lvl];
+              if (xf_u_less(next_uniform(), nw, cur_w)) {
+                free_slots |= 1u << t1_pslot;  // keep tree2's proposal, drop tree1's
               } else {
                 if (cur_pslot != kLeafProp) free_slots |= 1u << cur_pslot;
-                cur_pslot = st_pslot[lvl];
-                cur_pE = st_pE[lvl];
-                cur_plogp = st_plogp[lvl];
+                cur_pslot = t1_pslot;
+                cur_pE = ss->pE[lvl];
+                cur_plogp = ss->plogp[lvl];
               }
-              cur_ls = nls;
-              cur_lw = nlw;
+              cur_w = nw;
+              cur_a = na;
               if (turn) {
                 fail = 2;
                 break;
@@ -321,11 +334,18 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
                   vec(vid_stack(lvl, 2))[k * G] = cur_ps[k];
                 }
               }
-              st_ls[lvl] = cur_ls;
-              st_lw[lvl] = cur_lw;
-              st_pE[lvl] = cur_pE;
-              st_plogp[lvl] = cur_plogp;
-              st_pslot[lvl] = cur_pslot;
+              // One writer.  Readers see it after at least one group barrier (the next leaf's energy reduction) and
+              // finished reading the previous occupant before the barrier that preceded this point.
+              if (lane == 0) {
+                ss->wm[lvl] = cur_w.m;
+                ss->we[lvl] = cur_w.e;
+                ss->am[lvl] = cur_a.m;
+                ss->ae[lvl] = cur_a.e;
+                ss->pE[lvl] = cur_pE;
+                ss->plogp[lvl] = cur_plogp;
+                ss->pslot[lvl] = cur_pslot;
+              }
+              if constexpr (G == 32) __syncwarp();
             }
           }
           ++depth;              // nuts.py:315
@@ -336,7 +356,7 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
             break;
           }
           // ---- top of _Tree.extend (nuts.py:321-340): T = cur, T.left.p = cur_lp, T.right = z, T.p_sum = cur_ps
-          if (log(next_uniform()) < cur_ls - ls) {  // :321-323
+          if (xf_u_less(next_uniform(), xf_add(Wp, xf_one()), cur_w)) {  // logbern(tree.log_size - self.log_size) :321-323
             prop_E = cur_pE;
             prop_logp = cur_plogp;
             if (cur_pslot == kLeafProp) {
@@ -347,8 +367,8 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
               for (int k = 0; k < NP; ++k) vec(tail + T_PROPQ)[k * G] = vec(vid_prop(cur_pslot))[k * G];
             }
           }
-          ls = logaddexp(ls, cur_ls);      // :325
-          lwas = logaddexp(lwas, cur_lw);  // :326-328
+          Wp = xf_add(Wp, cur_w);    // log_size = logaddexp(log_size, tree.log_size)                     (:325)
+          Acc = xf_add(Acc, cur_a);  // log_weighted_accept_sum                                          (:326-328)
           double d6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
           for (int k = 0; k < NP; ++k) {
@@ -400,7 +420,8 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
         (void)turning;
         // _Tree.stats (nuts.py:419-435)
         double mta = 0.0;
-        if (ls > 0) mta = exp(lwas - (ls + log1mexp(ls)));  // logdiffexp(log_size, 0)
+        // log_size > 0 <=> exp(log_size) - 1 > 0 in double; exp(lwas - logdiffexp(log_size, 0)) = Acc / (exp(log_size) - 1)
+        if (xf_value(Wp) > 0.0) mta = xf_ratio(Acc, Wp);
         accept_stat = mta;
         stat_a = (double)depth;
         stat_b = (double)n_prop;
@@ -576,7 +597,7 @@ int launch(const lmc_sampler_args& a, const Target& tgt) {
 
   KernelCfg cfg;
   cfg.ws_vecs = KIND == KIND_NUTS ? ws_vecs_nuts(a.max_treedepth) : 0;
-  const size_t red_bytes = (size_t)CPB * 2 * Group<G>::kWarps * kRedSlots * sizeof(double);
+  const size_t red_bytes = (size_t)CPB * (2 * Group<G>::kWarps * kRedSlots * sizeof(double) + sizeof(StackScalars));
   const size_t vec_bytes = (size_t)VS * sizeof(double2);
   // shared-memory policy: give each CTA an equal share of the SM for the CTAs the register file can hold, and
   // fill it with the hottest scratch vectors (at most the stack part: edges / p_sum stay global).
