@@ -1,0 +1,354 @@
+"""bench.py -- leapfrog-steps/sec of the NUTS hot path (BASELINE.json's metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload headline|cfg2|cfg3|cfg4|cfg5]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (default "headline", the north star's target workload): NUTS, 1024 chains per GPU,
+1000-dim diagonal Gaussian (sigma_i = 10^linspace(-.5,.5)), QuadPotentialDiagAdapt + dual averaging, max_treedepth 10,
+in-kernel Philox randomness.  One STEP = one launch of the sampler kernel = `--trans-per-step` consecutive NUTS
+transitions of every chain (momentum draw, tree building, both adaptations, trace + statistics written to HBM),
+continuing one run: the first `--tune` transitions tune.  Only useful leapfrogs (sum of the `tree_size` statistic over
+the timed steps) are counted.  Weak scaling: every GPU runs its own block of chains, no collective while sampling,
+one NCCL all-gather of the last step's draws afterwards (timed separately, reported as `allgather_ms`).
+
+Timing: CUDA events on the launching stream around every timed step; a 512 MiB buffer is rewritten between steps to
+flush L2 (outside the events); barrier + synchronize before and after the timed region; max over ranks.
+`e2e` is one `littlemcmc_b200.sample()` call (the public API) for the same number of transitions with HOST buffers in
+and out: pinned start positions H2D, every draw of the trace and all statistics D2H, tuning included, wall clock.
+`cpu_baseline` / `--impl reference`: the NumPy oracle port of the reference sampler (oracle/lmc_oracle.py, bit-identical
+to eigenfoo/littlemcmc on the golden fixtures) on the box's host cores, one process per core, bounded sample.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (chains per GPU, ndim, target, max_treedepth, tune, description)
+    "headline": (1024, 1000, "gauss", 10, 200, "NUTS, 1024 chains/GPU x 1000-dim diagonal Gaussian, max_treedepth=10"),
+    "cfg2": (1024, 100, "gauss", 10, 200, "NUTS, 1024 chains x 100-dim diagonal Gaussian, max_treedepth=10"),
+    "cfg3": (4096, 1000, "illcond", 10, 500, "NUTS, 4096 chains x 1000-dim ill-conditioned Gaussian (kappa=1e4)"),
+    "cfg4": (8192, 50, "funnel", 12, 300, "NUTS, 8192 chains x 50-dim Neal's funnel, max_treedepth=12"),
+    "cfg5": (8192, 1000, "gauss", 10, 200, "NUTS, 8192 chains/GPU x 1000-dim diagonal Gaussian (65536 chains on 8 GPUs)"),
+}
+
+
+def make_target_np(kind, D):
+    """The oracle-side callable and the parameters of the fused target."""
+    from oracle import lmc_oracle as orc
+    if kind == "gauss":
+        sigma = 10 ** np.linspace(-0.5, 0.5, D)
+        return orc.diag_gaussian(1 / sigma**2), dict(tau=1 / sigma**2)
+    if kind == "illcond":
+        sig2 = 10 ** np.linspace(0, 4, D)
+        return orc.diag_gaussian(1 / sig2), dict(tau=1 / sig2)
+    return orc.neal_funnel(D), dict()
+
+
+# ---- CPU arm: the oracle port of the reference on the host cores -------------------------------------------------------
+def _cpu_worker(args):
+    kind, D, max_depth, n_trans, n_tune, seed = args
+    from oracle import lmc_oracle as orc
+    f, _ = make_target_np(kind, D)
+    smp = orc.Sampler(f, D, orc.DiagPotential(D, var=np.ones(D), initial_mean=np.zeros(D), initial_weight=10.0),
+                      kind="nuts", max_treedepth=max_depth)
+    rng = np.random.RandomState(seed)
+    t0 = time.perf_counter()
+    _, st = orc.sample_chain(smp, np.zeros(D), n_trans - n_tune, n_tune, rng)
+    dt = time.perf_counter() - t0
+    return float(st["tree_size"].sum()), dt
+
+
+def cpu_reference_step(kind, D, max_depth, n_trans, cores, seed0):
+    """One bounded sample: every core runs one chain for n_trans transitions.
+    -> (leapfrogs, slowest worker's seconds, sum of per-process leapfrog rates)."""
+    jobs = [(kind, D, max_depth, n_trans, n_trans, seed0 + i) for i in range(cores)]
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_cpu_worker, jobs)
+    # aggregate = sum of per-process rates, interpreter / pool start-up excluded
+    return sum(r[0] for r in res), max(r[1] for r in res), sum(r[0] / r[1] for r in res)
+
+
+def run_reference_arm(args, wl):
+    chains, D, kind, max_depth, tune, desc = wl
+    cores = os.cpu_count() or 1
+    # bounded: about 60 s of host work for the whole run whatever K is (a chain does ~150-400 transitions/s)
+    n_trans = args.cpu_trans or max(40, min(2000, int(60.0 * 250 / max(1, args.steps))))
+    for w in range(min(args.warmup, 2)):
+        cpu_reference_step(kind, D, max_depth, max(8, n_trans // 10), cores, 1000 + w)
+    tot_wall, rates = 0.0, []
+    for k in range(args.steps):
+        _, wall, rate = cpu_reference_step(kind, D, max_depth, n_trans, cores, 5000 + 97 * k)
+        rates.append(rate)
+        tot_wall += wall
+    value = float(np.mean(rates))
+    sample = "%d processes x 1 chain x %d tuning transitions per step (same target density, D=%d)" % (cores, n_trans, D)
+    line = {
+        "impl": "reference", "metric": "leapfrog-steps/sec (all chains)", "value": value, "unit": "leapfrog-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_wall / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s: %s" % (args.workload, desc), "ndim": D},
+        "cpu_baseline": {"value": value, "unit": "leapfrog-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "leapfrog-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---- clocks ------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Polls SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if mask & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ---- GPU arm -----------------------------------------------------------------------------------------------------------
+def run_gpu_arm(args, wl):
+    import torch
+    import torch.distributed as dist
+
+    import littlemcmc_b200 as lmc
+    from littlemcmc_b200 import _lib as L
+    from littlemcmc_b200 import engine
+
+    chains, D, kind, max_depth, tune, desc = wl
+    if args.chains:
+        chains = args.chains
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _, tparams = make_target_np(kind, D)
+    target = (lmc.targets.NealFunnel(D) if kind == "funnel" else lmc.targets.DiagGaussian(tau=tparams["tau"]))
+    tps = args.trans_per_step
+
+    def make_step():
+        pot = lmc.QuadPotentialDiagAdapt(D, np.zeros(D), np.ones(D), 10)
+        step = lmc.NUTS(target, D, potential=pot, max_treedepth=max_depth)
+        step._knobs = dict(group=args.group, smem_vecs=args.smem_vecs, max_slots=args.max_slots)
+        return step
+
+    # -- kernel-level measurement (inputs resident in HBM) ---------------------------------------------------------------
+    step = make_step()
+    seeds = 1_000_003 * (rank + 1) + np.arange(chains)          # distinct streams on every rank
+    ch = step._bind(chains, device=dev, seeds=seeds)
+    step.reset_tuning()
+    step.iter_count = 0
+    ch.set_position(np.zeros(D))
+    trace = torch.empty(chains, tps, D, dtype=torch.float64, device=dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(args.warmup):
+        step._run(tps, tune, trace=trace)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    evs, stats_keep = [], []
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()                                           # L2 flush, outside the timed events
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _, st = step._run(tps, tune, trace=trace)
+        e1.record()
+        evs.append((e0, e1))
+        stats_keep.append(st)
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    clocks.stop_flag = True
+    clocks.join()
+    if world > 1:
+        dist.barrier()
+    step._check_status()
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    dev_ms = float(sum(step_ms))
+    leap_per_step = [float(s[:, :, L.STAT_TREE_SIZE].sum().item()) for s in stats_keep]
+    leapfrogs = float(sum(leap_per_step))
+    depth_mean = float(torch.stack([s[:, :, L.STAT_DEPTH].mean() for s in stats_keep]).mean().item())
+    accept_mean = float(torch.stack([s[:, :, L.STAT_ACCEPT].mean() for s in stats_keep]).mean().item())
+    n_div = float(sum(s[:, :, L.STAT_DIVERGING].sum().item() for s in stats_keep))
+
+    # -- the single collective of the design: all-gather the last step's draws ---------------------------------------------
+    allgather_ms = None
+    if world > 1:
+        gathered = torch.empty(world * chains, tps, D, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(gathered, trace)           # warm-up (communicator setup)
+        torch.cuda.synchronize()
+        dist.barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        dist.all_gather_into_tensor(gathered, trace)
+        g1.record()
+        torch.cuda.synchronize()
+        allgather_ms = g0.elapsed_time(g1)
+        agg = torch.tensor([leapfrogs, dev_ms, allgather_ms], dtype=torch.float64, device=dev)
+        tot = agg.clone()
+        dist.all_reduce(tot[0:1], op=dist.ReduceOp.SUM)
+        mx = agg.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        leapfrogs_all, dev_ms_max, allgather_ms = float(tot[0]), float(mx[1]), float(mx[2])
+    else:
+        leapfrogs_all, dev_ms_max = leapfrogs, dev_ms
+    value = leapfrogs_all / (dev_ms_max * 1e-3)
+
+    # -- end to end through the public API with host buffers -----------------------------------------------------------------
+    n_e2e = args.steps * tps
+    e2e_tune = min(tune, n_e2e // 2)
+    start_host = torch.zeros(chains, D, dtype=torch.float64).pin_memory()
+    step2 = make_step()
+    lmc.sample(target, D, draws=tps, tune=tps, step=step2, chains=chains, start=start_host.numpy(),
+               random_seed=list(seeds), discard_tuned_samples=False, device=dev, progressbar=False)  # warm-up
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    tr_h, st_h = lmc.sample(target, D, draws=n_e2e - e2e_tune, tune=e2e_tune, step=step2, chains=chains,
+                            start=start_host.numpy(), random_seed=list(seeds + 17), discard_tuned_samples=False,
+                            device=dev, progressbar=False)
+    e2e_s = time.perf_counter() - t0
+    e2e_leap = float(st_h["tree_size"].sum())
+    if world > 1:
+        agg = torch.tensor([e2e_leap, e2e_s], dtype=torch.float64, device=dev)
+        tot, mx = agg.clone(), agg.clone()
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        e2e_leap, e2e_s = float(tot[0]), float(mx[1])
+    e2e_value = e2e_leap / e2e_s
+    h2d = (chains * D * 8 + chains * 8) / args.steps
+    d2h = (tr_h.nbytes + chains * n_e2e * L.NSTATS * 8) / args.steps
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # -- roofline of the dominant (only) kernel -------------------------------------------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    bytes_per_leapfrog = 48 * D                                 # read q,p,g + write q',p',g' in fp64
+    achieved = (leapfrogs / args.steps) * bytes_per_leapfrog / (dev_ms / args.steps * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(args.workload)
+
+    # -- CPU baseline on this box's host cores (bounded sample) ----------------------------------------------------------------
+    cores = os.cpu_count() or 1
+    cpu = None
+    if not args.no_cpu:
+        n_cpu = args.cpu_trans or 3000
+        _, _, cpu_rate = cpu_reference_step(kind, D, max_depth, n_cpu, cores, 4242)
+        cpu = {"value": cpu_rate, "unit": "leapfrog-steps/s", "cores": cores, "kind": "port",
+               "sample": "%d processes x 1 chain x %d tuning transitions of the same target (D=%d), sum of per-process "
+                         "rates, oracle/lmc_oracle.py" % (cores, n_cpu, D)}
+
+    line = {
+        "metric": "leapfrog-steps/sec (all chains)", "value": value, "unit": "leapfrog-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s: %s" % (args.workload, desc), "chains_per_gpu": chains, "ndim": D,
+                   "transitions_per_step": tps, "tune": tune, "rng": "in-kernel Philox4x32-10",
+                   "cache": "512 MiB buffer rewritten between timed steps (L2 flush outside the CUDA events)",
+                   "mean_tree_depth": depth_mean, "mean_tree_accept": accept_mean, "divergences": n_div,
+                   "leapfrogs_timed": leapfrogs_all, "wall_ms_incl_flush": t_wall * 1e3,
+                   "parallelism": "chains sharded x%d, no collective while sampling" % world},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src,
+                     "note": "achieved = algorithmic 48*D bytes per leapfrog x leapfrogs per launch / launch time; chain "
+                             "state is register/shared-memory resident, so measured DRAM traffic is far below it"},
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": "leapfrog-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "note": "one littlemcmc_b200.sample() call, %d transitions (%d tuning), pinned host start in, full host "
+                        "trace + stats out, wall clock %.1f ms" % (n_e2e, e2e_tune, e2e_s * 1e3)},
+        "gpu_launches": args.steps,
+        "clocks": clocks.summary(),
+    }
+    if allgather_ms is not None:
+        line["allgather_ms"] = allgather_ms
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS))
+    ap.add_argument("--trans-per-step", type=int, default=10)
+    ap.add_argument("--chains", type=int, default=0, help="override chains per GPU")
+    ap.add_argument("--cpu-trans", type=int, default=0, help="transitions per CPU-baseline chain (0 = bounded default)")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--group", type=int, default=0)
+    ap.add_argument("--smem-vecs", type=int, default=-1)
+    ap.add_argument("--max-slots", type=int, default=0)
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", 0)) != 0:
+            return
+        run_reference_arm(args, wl)
+        return
+    run_gpu_arm(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -200,6 +200,12 @@ int lmc_leapfrog_half2(int32_t n_chains, int32_t ndim, int64_t ld, const double*
 int lmc_rng_fill(const uint64_t* seeds, int32_t n_chains, int32_t ndim, int64_t iter0, int32_t n_trans,
                  int64_t u_stride, double* normals, double* uniforms, void* stream);
 
+/* Copy `height` rows of `width_bytes` from device memory (row pitch spitch) to pinned host memory (row pitch
+ * dpitch) on `stream`: how sample() streams blocks of the [chains, draws, ndim] trace out while sampling continues
+ * (the reference's `trace[:, i] = q`, sampling.py:513, followed by its host-side reshape :208). */
+int lmc_memcpy2d_d2h(void* dst_host, int64_t dpitch, const void* src_device, int64_t spitch, int64_t width_bytes,
+                     int64_t height, void* stream);
+
 /* Last CUDA error string seen by the library on this thread (host pointer, static storage). */
 const char* lmc_last_error(void);
 

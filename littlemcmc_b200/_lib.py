@@ -65,6 +65,7 @@ SYMBOLS = {
     "lmc_leapfrog_half1": (C.c_int, [_I32, _I32, _I64, _P, _P, _P, _P, _P, _P, _I64, _P]),
     "lmc_leapfrog_half2": (C.c_int, [_I32, _I32, _I64, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P]),
     "lmc_rng_fill": (C.c_int, [_P, _I32, _I32, _I64, _I32, _I64, _P, _P, _P]),
+    "lmc_memcpy2d_d2h": (C.c_int, [_P, _I64, _P, _I64, _I64, _I64, _P]),
     "lmc_last_error": (C.c_char_p, []),
 }
 

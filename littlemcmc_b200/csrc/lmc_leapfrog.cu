@@ -265,3 +265,13 @@ extern "C" int lmc_rng_fill(const uint64_t* seeds, int32_t n_chains, int32_t ndi
   LMC_CUDA(cudaGetLastError());
   return LMC_OK;
 }
+
+extern "C" int lmc_memcpy2d_d2h(void* dst, int64_t dpitch, const void* src, int64_t spitch, int64_t width_bytes,
+                                int64_t height, void* stream) {
+  if (!dst || !src || width_bytes < 0 || height < 0 || dpitch < width_bytes || spitch < width_bytes)
+    return LMC_ERR_BADARG;
+  if (width_bytes == 0 || height == 0) return LMC_OK;
+  LMC_CUDA(cudaMemcpy2DAsync(dst, (size_t)dpitch, src, (size_t)spitch, (size_t)width_bytes, (size_t)height,
+                             cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return LMC_OK;
+}

@@ -1,0 +1,166 @@
+"""Sampling driver: mirror of reference sampling.py (`sample` :35-222, `init_nuts` :524-605).
+
+The reference runs chains one after another (or one OS process per chain) and, inside each, a Python loop over draws
+(sampling.py:370, :507).  Here all chains advance together on the GPU and the draw loop is inside the kernel: the
+driver issues a handful of launches (blocks of transitions) and copies finished blocks of the trace to pinned host
+memory on a side stream while the next block runs.
+
+Seeding follows the reference exactly on the host (np.random.seed(random_seed); one randint(2**30) per chain,
+sampling.py:131-134; init_nuts reseeds with the first one and draws the single jittered start, :574-584).  The
+per-chain seeds then key per-chain Philox streams on the device, so results do not depend on how chains are
+distributed over GPUs.
+"""
+import logging
+import os
+from collections.abc import Iterable
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .hmc import HamiltonianMC  # noqa: F401
+from .nuts import NUTS
+from .quadpotential import QuadPotentialDiagAdapt
+
+_log = logging.getLogger("littlemcmc_b200")
+
+
+def _resolve_seeds(random_seed, chains):
+    """reference sampling.py:131-138."""
+    if random_seed is None or isinstance(random_seed, (int, np.integer)):
+        if random_seed is not None:
+            np.random.seed(int(random_seed))
+        return [int(np.random.randint(2 ** 30)) for _ in range(chains)]
+    if isinstance(random_seed, Iterable):
+        seeds = [int(s) for s in random_seed]
+        if len(seeds) < chains:
+            raise ValueError("need one random seed per chain")
+        return seeds[:chains]
+    raise TypeError("Invalid value for `random_seed`. Must be tuple, list or int")
+
+
+def sample(logp_dlogp_func, model_ndim, draws=1000, tune=1000, step=None, init="auto", chains=None, cores=None,
+           start=None, progressbar=True, random_seed=None, discard_tuned_samples=True, chain_idx=0, callback=None,
+           mp_ctx=None, pickle_backend="pickle", device=None, block=None, return_device=False, **kwargs):
+    """Draw samples with the given step method; signature and return value of reference `sample` (sampling.py:35-222).
+
+    Returns ``(trace, stats)``: ``trace`` float64 ``[chains, draws, model_ndim]``; ``stats`` a dict of arrays
+    ``[chains, draws, 1]`` with the dtypes of ``step.stats_dtypes[0]``.
+
+    Differences a caller can observe: ``cores``, ``mp_ctx``, ``pickle_backend`` and ``progressbar`` are accepted and
+    ignored (chains are a tensor dimension, there are no worker processes); ``start`` may also be ``[chains, ndim]``.
+    Extra keywords: ``device`` (CUDA device, default current), ``block`` (transitions per launch, default: sized so a
+    trace block is <= 1 GiB), ``return_device`` (keep results as torch tensors on the GPU and skip the host copy).
+    """
+    if cores is None:
+        cores = min(4, os.cpu_count() or 1)
+    if chains is None:
+        chains = max(2, cores)                                                      # sampling.py:124-128
+    seeds = _resolve_seeds(random_seed, chains)
+    if draws == 0:
+        _log.warning("Tuning was enabled throughout the whole trace.")
+    elif draws < 500:
+        _log.warning("Only %d samples in chain.", draws)
+
+    if step is None or start is None:                                               # sampling.py:148-159
+        start_, step_ = init_nuts(logp_dlogp_func=logp_dlogp_func, model_ndim=model_ndim, init=init,
+                                  random_seed=seeds, **kwargs)
+        step = step_ if step is None else step
+        start = start_ if start is None else start
+    start = np.asarray(start, dtype="d")
+    if start.ndim == 1:
+        start = np.broadcast_to(start, (chains, model_ndim))                        # one start for all chains (:163-164)
+
+    T = int(tune) + int(draws)
+    ch = step._bind(chains, device=device, seeds=seeds)
+    step.tune = bool(tune)                                                          # sampling.py:503
+    step.reset_tuning()                                                             # :504-505, for every chain
+    step.iter_count = 0                                                             # :508-509
+    ch.status.zero_()
+    ch.set_position(start)
+    dev, D = ch.device, int(model_ndim)
+
+    keep_from = int(tune) if discard_tuned_samples else 0
+    n_keep = T - keep_from
+    if block is None:
+        block = max(1, min(T, (1 << 30) // max(1, chains * D * 8)))
+    if return_device:
+        trace_out = torch.empty(chains, n_keep, D, dtype=torch.float64, device=dev)
+        host_trace = None
+    else:
+        trace_out = None
+        host_trace = torch.empty(chains, n_keep, D, dtype=torch.float64, pin_memory=True)
+    compute = torch.cuda.current_stream(dev)
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs, copy_done = [None, None], [None, None]      # double-buffered device blocks of the trace
+    stats_blocks = []
+    done, blk = 0, 0
+    while done < T:
+        n = min(block, T - done)
+        if done < keep_from < done + n:
+            n = keep_from - done                       # a block never straddles the discard boundary
+        kept = done >= keep_from
+        if kept and return_device:
+            tr_view = trace_out[:, done - keep_from:done - keep_from + n]
+            _, st = step._run(n, int(tune), trace=tr_view)
+        else:
+            i = blk & 1
+            if bufs[i] is None:
+                bufs[i] = torch.empty(chains, min(block, T), D, dtype=torch.float64, device=dev)
+            if copy_done[i] is not None:
+                compute.wait_event(copy_done[i])       # the previous copy out of this buffer must have finished
+            tr_view = bufs[i][:, :n]
+            _, st = step._run(n, int(tune), trace=tr_view)
+            if kept:
+                ready = torch.cuda.Event()
+                ready.record(compute)
+                copy_stream.wait_event(ready)
+                dst = host_trace[:, done - keep_from:done - keep_from + n]
+                # [chains] rows of n*D contiguous doubles each, different pitches on the two sides
+                L.check(L.load().lmc_memcpy2d_d2h(dst.data_ptr(), dst.stride(0) * 8, tr_view.data_ptr(),
+                                                  tr_view.stride(0) * 8, n * D * 8, chains,
+                                                  copy_stream.cuda_stream), "lmc_memcpy2d_d2h")
+                copy_done[i] = torch.cuda.Event()
+                copy_done[i].record(copy_stream)
+        stats_blocks.append(st)
+        done += n
+        blk += 1
+    compute.synchronize()
+    copy_stream.synchronize()
+    step._check_status()
+    if tune < T:
+        step.stop_tuning()                                                          # sampling.py:510-511
+    stats_dev = torch.cat(stats_blocks, 1) if len(stats_blocks) > 1 else stats_blocks[0]
+    step._account(stats_dev, int(tune))
+
+    stats_kept = stats_dev[:, keep_from:]
+    if return_device:
+        stats = {name: stats_kept[:, :, col].unsqueeze(-1) for name, col in step._stat_columns.items()}
+        return trace_out, stats
+    sh = stats_kept.cpu().numpy()
+    stats = {name: sh[:, :, step._stat_columns[name]][:, :, None].astype(dtype)
+             for name, dtype in step.stats_dtypes[0].items()}                       # sampling.py:212-220
+    return host_trace.numpy(), stats
+
+
+def init_nuts(logp_dlogp_func, model_ndim, init="auto", random_seed=None, **kwargs):
+    """Mass-matrix initialisation for NUTS: reference sampling.py:524-605 (diagonal initialisers)."""
+    if not isinstance(init, str):
+        raise TypeError("init must be a string.")
+    init = init.lower()
+    if init == "auto":
+        init = "jitter+adapt_diag"
+    _log.info("Initializing NUTS using %s...", init)
+    if random_seed is not None:
+        np.random.seed(int(np.atleast_1d(random_seed)[0]))                          # :574-576
+    if init == "adapt_diag":
+        start = np.zeros(model_ndim)
+    elif init == "jitter+adapt_diag":
+        start = 2 * np.random.rand(model_ndim) - 1                                  # :584
+    elif init in ("adapt_full", "jitter+adapt_full"):
+        raise NotImplementedError("dense mass-matrix adaptation is outside the B200 hot path (SURVEY.md section 8f)")
+    else:
+        raise ValueError("Unknown initializer: {}.".format(init))
+    potential = QuadPotentialDiagAdapt(model_ndim, start, np.ones(model_ndim), 10)  # :582,587
+    step = NUTS(logp_dlogp_func=logp_dlogp_func, model_ndim=model_ndim, potential=potential, **kwargs)
+    return start, step

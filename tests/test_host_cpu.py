@@ -1,0 +1,117 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/lmc_b200.h declares, and the host logic
+(seeding, validation, shape selection) behaves like the reference's.  No compute calls (no GPU here)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    ge.build()
+    from littlemcmc_b200 import _lib
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from littlemcmc_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "lmc_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(lmc_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.lmc_abi_version() == _lib.ABI_VERSION
+
+
+def test_struct_layout_matches_header(lib):
+    """sizeof(lmc_sampler_args) as nvcc lays it out == the ctypes mirror (checked through a bad-arg call that must
+    come back as LMC_ERR_BADARG, not crash, and by the field offsets being naturally aligned)."""
+    import ctypes as C
+    from littlemcmc_b200 import _lib as L
+    a = L.SamplerArgs()
+    assert C.sizeof(L.Target) == 24 and C.sizeof(L.Rng) == 40
+    for name, _ in L.SamplerArgs._fields_:
+        off = getattr(L.SamplerArgs, name).offset
+        size = getattr(L.SamplerArgs, name).size
+        assert off % min(size, 8) == 0, name
+    a.abi_version = L.ABI_VERSION + 1
+    assert lib.lmc_nuts_sample(C.byref(a)) == L.ERR_BADARG
+    assert lib.lmc_hmc_sample(None) == L.ERR_BADARG
+
+
+def test_workspace_bytes_is_host_only(lib):
+    from littlemcmc_b200 import _lib as L
+    n = lib.lmc_workspace_bytes(L.KIND_NUTS, 1024, 1000, 10, 0)
+    assert n > 0 and n % 16 == 0
+    assert lib.lmc_workspace_bytes(L.KIND_NUTS, 1024, 1000, 17, 0) == L.ERR_UNSUPPORTED
+    assert lib.lmc_workspace_bytes(L.KIND_NUTS, 8, 10 ** 6, 10, 0) == L.ERR_UNSUPPORTED
+    assert lib.lmc_workspace_bytes(L.KIND_HMC, 8, 10, 10, 0) > 0
+
+
+def test_seed_resolution_matches_reference_semantics():
+    """sampling.py:131-138: int seed -> np.random.seed + one randint(2**30) per chain; list -> truncated."""
+    from littlemcmc_b200.sampling import _resolve_seeds
+    np.random.seed(123)
+    expect = [int(np.random.randint(2 ** 30)) for _ in range(4)]
+    assert _resolve_seeds(123, 4) == expect
+    assert _resolve_seeds([9, 8, 7, 6, 5], 3) == [9, 8, 7]
+    with pytest.raises(TypeError):
+        _resolve_seeds(1.5, 2)
+
+
+def test_init_nuts_start_is_the_reference_start():
+    """init_nuts reseeds with the first chain seed and draws 2*rand(D)-1 (sampling.py:574-584)."""
+    import littlemcmc_b200 as lmc
+    tgt = lmc.targets.StdNormal(5)
+    start, step = lmc.init_nuts(tgt, 5, init="jitter+adapt_diag", random_seed=[77, 78])
+    np.random.seed(77)
+    assert np.array_equal(start, 2 * np.random.rand(5) - 1)
+    assert step.potential._initial_weight == 10 and np.array_equal(step.potential._initial_mean, start)
+    assert step.step_size == 0.25 / 5 ** 0.25
+    s2, _ = lmc.init_nuts(tgt, 5, init="adapt_diag")
+    assert np.array_equal(s2, np.zeros(5))
+    with pytest.raises(ValueError):
+        lmc.init_nuts(tgt, 5, init="nope")
+    with pytest.raises(TypeError):
+        lmc.init_nuts(tgt, 5, init=3)
+
+
+def test_potential_validation():
+    import littlemcmc_b200 as lmc
+    from littlemcmc_b200.quadpotential import PositiveDefiniteError
+    with pytest.raises(PositiveDefiniteError):
+        lmc.quad_potential(np.array([1.0, -1.0]), True)
+    with pytest.raises(ValueError):
+        lmc.QuadPotentialDiagAdapt(3, np.zeros(2))
+    with pytest.raises(ValueError):
+        lmc.QuadPotentialDiagAdapt(3, np.zeros(3), np.ones((3, 3)))
+    with pytest.raises(ValueError):
+        lmc.NUTS(lmc.targets.StdNormal(2), 2, scaling=np.ones(2), potential=lmc.QuadPotentialDiag(np.ones(2)))
+    pot = lmc.QuadPotentialDiagAdapt(3, np.zeros(3))          # initial_diag None -> ones, weight 1 (:178-180)
+    assert pot._initial_weight == 1 and np.array_equal(pot._initial_diag, np.ones(3))
+
+
+def test_targets_are_reference_style_callbacks():
+    """The fused targets are plain logp_dlogp_func callables; gradients checked by finite differences."""
+    import littlemcmc_b200 as lmc
+    rs = np.random.RandomState(0)
+    for tgt, D in ((lmc.targets.DiagGaussian(sigma=rs.rand(6) + 0.5), 6), (lmc.targets.NealFunnel(6), 6)):
+        q = rs.randn(D) * 0.5
+        lp, g = tgt(q)
+        for i in range(D):
+            e = np.zeros(D); e[i] = 1e-6  # noqa: E702
+            fd = (tgt(q + e)[0] - tgt(q - e)[0]) / 2e-6
+            assert abs(fd - g[i]) < 1e-5 * max(1, abs(g[i]))
+
+
+def test_no_cpu_fallback():
+    """Binding chains to a non-CUDA device must fail loudly."""
+    from littlemcmc_b200 import _lib as L, engine
+    with pytest.raises(L.LmcError):
+        engine.DeviceChains(2, 3, "cpu")
