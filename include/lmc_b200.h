@@ -195,6 +195,38 @@ int lmc_leapfrog_half2(int32_t n_chains, int32_t ndim, int64_t ld, const double*
                        double* p, double* v, const double* g_new, const double* logp, const double* var,
                        int64_t var_stride, double* energy, void* stream);
 
+/*
+ * Callback mode: the same transitions around an EXTERNAL gradient -- the user's logp_dlogp_func (base_hmc.py:34,
+ * called at integration.py:62 and :115) evaluated by the caller as one batched op over all chains between two
+ * launches.  Every chain is a resumable state machine kept in `machine`:
+ *     lmc_callback_begin(kind, &c);                         // q_eval <- base.q, every chain asks for its first gradient
+ *     while (*n_running > 0) {                              // host reads the device counter now and then
+ *         logp_eval[c], g_eval[c, :] = f(q_eval[c, :]);     // caller's op, all chains, same stream
+ *         lmc_callback_advance(kind, &c);                   // each chain consumes its gradient and runs to the next
+ *     }                                                     // point where it needs one (or finishes)
+ * Chains are not in lock step (one may be deep in a tree while another starts its next draw); finished chains idle.
+ * `base.target` and `base.workspace` are ignored; everything else in `base` means what it means for lmc_nuts_sample
+ * (state arrays updated in place, trace / stats / status written per transition, TAPE or PHILOX randomness).
+ */
+typedef struct lmc_callback_args {
+  lmc_sampler_args base;
+  double* q_eval;          /* [n_chains, ld] out: where the callback must be evaluated next (padding = 0)        */
+  const double* g_eval;    /* [n_chains, ld] in : dlogp at q_eval (padding ignored)                              */
+  const double* logp_eval; /* [n_chains]     in : logp at q_eval                                                 */
+  void* machine;           /* >= lmc_callback_state_bytes(...) bytes, 16-byte aligned, owned by the caller       */
+  int64_t machine_bytes;
+  int32_t* n_running;      /* device counter: chains that still need gradient evaluations                        */
+} lmc_callback_args;
+
+/* Bytes of per-chain machine state for callback mode (host call).  `kind`: 0 = NUTS, 1 = HMC. */
+int64_t lmc_callback_state_bytes(int32_t kind, int32_t n_chains, int32_t ndim, int32_t max_treedepth);
+/* Start `base.n_trans` transitions of every chain: replaces the entry of BaseHMC._astep (base_hmc.py:140-143). */
+int lmc_callback_begin(int32_t kind, const lmc_callback_args* args);
+/* Consume (logp_eval, g_eval) and advance every chain to its next evaluation point: replaces the code between two
+ * logp_dlogp_func calls of the reference (integration.py:116-119 -> nuts.py:352-417 / 315-340 -> base_hmc.py:161-190 ->
+ * integration.py:105-112). */
+int lmc_callback_advance(int32_t kind, const lmc_callback_args* args);
+
 /* Dump the numbers the PHILOX mode would consume into tapes (tests: Philox path == tape path == oracle).
  * normals: [n_chains, n_trans, ndim]; uniforms: [n_chains, n_trans, u_stride]. */
 int lmc_rng_fill(const uint64_t* seeds, int32_t n_chains, int32_t ndim, int64_t iter0, int32_t n_trans,

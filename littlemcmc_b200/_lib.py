@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblmc_b200.so")
+LIB_PATH = os.environ.get("LMC_LIB_PATH") or os.path.join(_HERE, "liblmc_b200.so")  # env: kernel experiments only
 
 ABI_VERSION = 1
 OK, ERR_BADARG, ERR_UNSUPPORTED, ERR_LAUNCH, ERR_WORKSPACE = 0, -1, -2, -3, -4
@@ -52,6 +52,11 @@ class SamplerArgs(C.Structure):
     ]
 
 
+class CallbackArgs(C.Structure):
+    _fields_ = [("base", SamplerArgs), ("q_eval", C.c_void_p), ("g_eval", C.c_void_p), ("logp_eval", C.c_void_p),
+                ("machine", C.c_void_p), ("machine_bytes", C.c_int64), ("n_running", C.c_void_p)]
+
+
 # every symbol include/lmc_b200.h declares: (restype, argtypes)
 _P, _I32, _I64 = C.c_void_p, C.c_int32, C.c_int64
 SYMBOLS = {
@@ -59,6 +64,9 @@ SYMBOLS = {
     "lmc_workspace_bytes": (_I64, [_I32, _I32, _I32, _I32, _I32]),
     "lmc_nuts_sample": (C.c_int, [C.POINTER(SamplerArgs)]),
     "lmc_hmc_sample": (C.c_int, [C.POINTER(SamplerArgs)]),
+    "lmc_callback_state_bytes": (_I64, [_I32, _I32, _I32, _I32]),
+    "lmc_callback_begin": (C.c_int, [_I32, C.POINTER(CallbackArgs)]),
+    "lmc_callback_advance": (C.c_int, [_I32, C.POINTER(CallbackArgs)]),
     "lmc_compute_state": (C.c_int, [C.POINTER(Target), _I32, _I32, _I64, _P, _P, _P, _I64, _P, _P, _P, _P, _P]),
     "lmc_leapfrog_step": (C.c_int, [C.POINTER(Target), _I32, _I32, _I64, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P,
                                     _P, _P, _P]),

@@ -73,11 +73,7 @@ class BaseHMC:
 
     def _fused_target(self):
         fused = fused_descriptor(self._logp_dlogp_func)
-        if fused is None:
-            raise NotImplementedError(
-                "this callback has no fused kernel; wrap device callbacks in targets.TorchBatched and use "
-                "integrator.step(), or use a built-in target (targets.DiagGaussian, targets.NealFunnel)")
-        if fused.ndim != self.model_ndim:
+        if fused is not None and fused.ndim != self.model_ndim:
             raise ValueError("target has %d dimensions, step method %d" % (fused.ndim, self.model_ndim))
         return fused
 
@@ -90,10 +86,21 @@ class BaseHMC:
     # ---- batched driver entry ----------------------------------------------------------------------------------------
     def _run(self, n_trans, n_tune, tapes=None, trace=None, stats=None):
         """`n_trans` transitions of every chain starting at `self.iter_count`; transitions with index < `n_tune` tune.
-        Returns device tensors (trace [C, n_trans, D], stats [C, n_trans, NSTATS]); asynchronous."""
-        tr, st = engine.run_transitions(self._kind, self._chains, self._fused_target(), n_trans=n_trans,
-                                        iter0=self.iter_count, n_tune=n_tune, params=self._params(),
-                                        seeds=self._seeds, tapes=tapes, trace=trace, stats=stats, knobs=self._knobs)
+        Returns device tensors (trace [C, n_trans, D], stats [C, n_trans, NSTATS]).
+
+        A target with a fused descriptor (targets.DiagGaussian / NealFunnel) runs whole transitions inside one kernel
+        launch (asynchronous).  Any other callback -- a targets.TorchBatched device op, or the reference's per-chain
+        NumPy callable -- runs in callback mode: the callback is evaluated for all chains between two launches
+        (engine.CallbackRun); that path returns when every chain has finished."""
+        fused = self._fused_target()
+        common = dict(n_trans=n_trans, iter0=self.iter_count, n_tune=n_tune, params=self._params(), seeds=self._seeds,
+                      tapes=tapes, trace=trace, stats=stats)
+        if fused is not None:
+            tr, st = engine.run_transitions(self._kind, self._chains, fused, knobs=self._knobs, **common)
+        else:
+            graph = bool(getattr(self._logp_dlogp_func, "cuda_graph", False))
+            tr, st = engine.run_transitions_callback(self._kind, self._chains, self._logp_dlogp_func, cuda_graph=graph,
+                                                     **common)
         self.iter_count += n_trans
         return tr, st
 

@@ -170,6 +170,12 @@ struct Group {
   }
 };
 
+// barrier over the threads of one group (G == 32: the warp; G >= 64: the whole CTA)
+template <int G>
+__device__ __forceinline__ void group_barrier() {
+  if constexpr (G == 32) __syncwarp(); else __syncthreads();
+}
+
 // ---- built-in target densities -----------------------------------------------------------------------------------
 // Protocol (all methods are called by every thread of the group with its own NP pairs):
 //   kPre            number of sums needed BEFORE the gradient can be formed (0 or 2)
@@ -292,6 +298,21 @@ __device__ __forceinline__ void load_row(const double* row, int lane, int ldh, d
   for (int k = 0; k < NP; ++k) {
     const int j = lane + k * G;
     x[k] = (j < ldh) ? r[j] : make_double2(0.0, 0.0);
+  }
+}
+// 128-bit load that bypasses L1 (ld.global.cg): for rows another SM may have written since this SM last read them
+__device__ __forceinline__ double2 ldcg2(const double2* p) {
+  double2 v;
+  asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+template <int G, int NP>
+__device__ __forceinline__ void load_row_cg(const double* row, int lane, int ldh, double2 (&x)[NP]) {
+  const double2* r = reinterpret_cast<const double2*>(row);
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    const int j = lane + k * G;
+    x[k] = (j < ldh) ? ldcg2(r + j) : make_double2(0.0, 0.0);
   }
 }
 template <int G, int NP>

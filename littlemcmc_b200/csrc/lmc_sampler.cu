@@ -9,7 +9,7 @@ static int check_args(const lmc_sampler_args* a, int kind) {
   if (a->abi_version != LMC_ABI_VERSION) return LMC_ERR_BADARG;
   if (a->n_chains < 0 || a->ndim < 1 || a->n_trans < 0) return LMC_ERR_BADARG;
   if (a->ld < a->ndim || (a->ld & 1)) return LMC_ERR_BADARG;
-  if (!a->q || !a->var || !a->adapt || !a->trace || !a->stats || !a->status) return LMC_ERR_BADARG;
+  if (!a->q || !a->var || !a->adapt || !a->trace || !a->stats || !a->status || !a->workspace) return LMC_ERR_BADARG;
   if (((uintptr_t)a->q | (uintptr_t)a->var | (uintptr_t)a->workspace) & 15) return LMC_ERR_BADARG;
   if (a->adapt_mass) {
     if (!a->mean_fg || !a->rawvar_fg || !a->mean_bg || !a->rawvar_bg) return LMC_ERR_BADARG;
@@ -26,7 +26,6 @@ static int check_args(const lmc_sampler_args* a, int kind) {
   if (kind == KIND_NUTS) {
     if (a->max_treedepth < 1 || a->max_treedepth > kMaxDepth) return LMC_ERR_UNSUPPORTED;
     if (a->early_max_treedepth < 0 || a->early_max_treedepth > kMaxDepth) return LMC_ERR_UNSUPPORTED;
-    if (!a->workspace) return LMC_ERR_BADARG;
   } else {
     if (a->max_steps < 1) return LMC_ERR_BADARG;
   }
@@ -60,7 +59,8 @@ static int sample_entry(const lmc_sampler_args* a, int kind) {
 
 extern "C" int64_t lmc_workspace_bytes(int32_t kind, int32_t n_chains, int32_t ndim, int32_t max_treedepth,
                                        int32_t tune_group) {
-  if (kind == lmc::KIND_HMC) return 16;
+  if (n_chains < 0) return LMC_ERR_BADARG;
+  if (kind == lmc::KIND_HMC) return (int64_t)lmc::sched_bytes(n_chains);
   if (kind != lmc::KIND_NUTS || max_treedepth < 1 || max_treedepth > lmc::kMaxDepth) return LMC_ERR_UNSUPPORTED;
   lmc::Shape s;
   if (!lmc::pick_shape(ndim, tune_group, &s)) return LMC_ERR_UNSUPPORTED;
@@ -73,7 +73,8 @@ extern "C" int64_t lmc_workspace_bytes(int32_t kind, int32_t n_chains, int32_t n
   const long long by_chains = (((long long)n_chains + cpb - 1) / cpb) * cpb;
   if (slots > by_chains) slots = by_chains;
   if (slots < cpb) slots = cpb;
-  return slots * lmc::ws_vecs_nuts(max_treedepth) * (long long)(s.G * s.NP) * (long long)sizeof(double2);
+  return (long long)lmc::sched_bytes(n_chains) +
+         slots * lmc::ws_vecs_nuts(max_treedepth) * (long long)(s.G * s.NP) * (long long)sizeof(double2);
 }
 
 extern "C" int lmc_nuts_sample(const lmc_sampler_args* args) { return lmc::sample_entry(args, lmc::KIND_NUTS); }

@@ -20,33 +20,11 @@
 
 #include "lmc_common.h"
 #include "lmc_device.cuh"
+#include "lmc_tree.cuh"
 
 namespace lmc {
 
 enum { KIND_NUTS = 0, KIND_HMC = 1 };
-constexpr int kLeafProp = -1;  // "the proposal is the current leaf, still in registers"
-
-// scratch-vector ids (ordered hottest first; ids < n_smem_vecs are shared-memory resident)
-//   0                 stack level 0: p  (left.p == right.p == p_sum for a single leaf)
-//   1, 2              proposal slots 0, 1
-//   3+4(l-1)+{0,1,2}  stack level l >= 1: left.p, right.p, p_sum
-//   3+4(l-1)+3        proposal slot l+1
-//   tail              trajectory edges L(q,p,g), R(q,p,g), trajectory p_sum, trajectory proposal q
-__host__ __device__ constexpr int vid_stack(int level, int which) { return level == 0 ? 0 : 3 + 4 * (level - 1) + which; }
-__host__ __device__ constexpr int vid_prop(int slot) { return slot < 2 ? 1 + slot : 4 * slot - 2; }
-__host__ __device__ constexpr int vid_tail(int max_depth) { return max_depth < 1 ? 3 : 4 * max_depth - 1; }
-enum { T_LQ = 0, T_LP, T_LG, T_RQ, T_RP, T_RG, T_PSUM, T_PROPQ, T_COUNT };
-__host__ __device__ constexpr int ws_vecs_nuts(int max_depth) { return vid_tail(max_depth) + T_COUNT; }
-
-// per-level scalars of the subtree stack, one copy per chain in shared memory (written by lane 0 only; every read
-// is separated from the write by a group barrier / __syncwarp, see the push below)
-struct StackScalars {
-  double wm[kMaxDepth], am[kMaxDepth];   // mantissas of exp(log_size), exp(log_weighted_accept_sum)
-  double pE[kMaxDepth], plogp[kMaxDepth];  // proposal energy / model_logp
-  int we[kMaxDepth], ae[kMaxDepth];      // exponents
-  int pslot[kMaxDepth];                  // proposal slot
-  int pad[kMaxDepth];
-};
 
 struct KernelCfg {
   int n_smem_vecs;  // scratch vectors per group kept in shared memory
@@ -56,11 +34,56 @@ struct KernelCfg {
 template <int G>
 __host__ __device__ constexpr int block_threads() { return G >= 64 ? G : 128; }
 
+// ---- work scheduler ----------------------------------------------------------------------------------------------
+// The unit of work is ONE transition of ONE chain.  Chains wait in a FIFO ring in the workspace header; a resident
+// thread group pops a chain, runs its next transition, writes the chain's state back to HBM and pushes the chain
+// to the tail.  Trees differ in size by orders of magnitude between chains and draws (1 .. 2^max_treedepth
+// leapfrogs), and the number of chains is rarely a multiple of the resident groups: with a static chain -> group
+// assignment the launch lasts as long as its unluckiest group, with the FIFO every group stays busy until the
+// queue drains.  Results do not depend on the schedule: all randomness is a function of (chain seed, iteration).
+//   header: unsigned head, tail, pad[2];  unsigned long long ring[n_chains] = (ticket + 1) << 32 | dead << 31 | chain;
+//           int prog[n_chains] = index of the chain's next transition within this call
+// A chain is in the ring at most once, so a ring of n_chains entries never overwrites an unread entry.
+struct SchedView {
+  unsigned* ctr;             // [0] = head (pop tickets), [1] = tail (push tickets)
+  unsigned long long* ring;  // [n_chains]
+  int* prog;                 // [n_chains]
+};
+__host__ __device__ inline size_t sched_bytes(int n_chains) {
+  return (((size_t)16 + (size_t)n_chains * 12) + 255) & ~(size_t)255;
+}
+__host__ __device__ inline SchedView sched_view(void* workspace, int n_chains) {
+  unsigned* c = reinterpret_cast<unsigned*>(workspace);
+  unsigned long long* r = reinterpret_cast<unsigned long long*>(c + 4);
+  return SchedView{c, r, reinterpret_cast<int*>(r + n_chains)};
+}
+constexpr unsigned kDeadBit = 0x80000000u;
+
+static __global__ void sched_init_kernel(void* workspace, int n_chains) {
+  const SchedView sv = sched_view(workspace, n_chains);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) {
+    sv.ctr[0] = 0u;
+    sv.ctr[1] = (unsigned)n_chains;
+  }
+  if (i < n_chains) {
+    sv.ring[i] = ((unsigned long long)(i + 1) << 32) | (unsigned)i;
+    sv.prog[i] = 0;
+  }
+}
+
+
 // Instantiated (threads per chain, pairs per thread, min resident CTAs per SM).  The third column caps registers:
 // 65536 / (block_threads * min_ctas) per thread.
+#ifndef LMC_MC_128_4
+#define LMC_MC_128_4 3
+#endif
+#ifndef LMC_MC_256_2
+#define LMC_MC_256_2 2
+#endif
 #define LMC_SHAPES(X) \
-  X(32, 1, 4) X(32, 2, 4) X(32, 4, 3) X(64, 4, 4) X(64, 8, 4) X(128, 2, 4) X(128, 4, 3) X(256, 2, 2) X(256, 4, 1) \
-  X(512, 2, 1) X(512, 4, 1) X(1024, 4, 1)
+  X(32, 1, 4) X(32, 2, 4) X(32, 4, 3) X(64, 4, 4) X(64, 8, 4) X(128, 2, 4) X(128, 4, LMC_MC_128_4) \
+  X(256, 2, LMC_MC_256_2) X(256, 4, 1) X(512, 2, 1) X(512, 4, 1) X(1024, 4, 1)
 
 template <int G, int NP>
 __host__ __device__ constexpr int min_ctas() {
@@ -81,45 +104,82 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
   const int gib = threadIdx.x / G;
   const int lane = threadIdx.x - gib * G;
   const int slot = blockIdx.x * CPB + gib;
-  const int n_slots = gridDim.x * CPB;
-  double2* const sm = smem2 + (size_t)gib * cfg.n_smem_vecs * VS;
   double* const red = reinterpret_cast<double*>(smem2 + (size_t)CPB * cfg.n_smem_vecs * VS) +
                       gib * (2 * Group<G>::kWarps * kRedSlots);
   StackScalars* const ss = reinterpret_cast<StackScalars*>(
       reinterpret_cast<double*>(smem2 + (size_t)CPB * cfg.n_smem_vecs * VS) + CPB * (2 * Group<G>::kWarps * kRedSlots)) + gib;
-  double2* const ws = reinterpret_cast<double2*>(a.workspace) + (size_t)slot * cfg.ws_vecs * VS;
+  Scratch<G, NP> sc;
+  sc.sm = smem2 + (size_t)gib * cfg.n_smem_vecs * VS;
+  sc.ws = reinterpret_cast<double2*>(reinterpret_cast<char*>(a.workspace) + sched_bytes(a.n_chains)) +
+          (size_t)slot * cfg.ws_vecs * VS;
+  sc.n_smem = cfg.n_smem_vecs;
+  sc.lane = lane;
+  __shared__ int s_pop[2];
   Group<G> grp(lane, red);
+  const SchedView sv = sched_view(a.workspace, a.n_chains);
+  const unsigned total_units = (unsigned)a.n_chains * (unsigned)a.n_trans;
 
   const int D = a.ndim;
   const int ldh = (int)(a.ld >> 1);
-  const int n_smem = cfg.n_smem_vecs;
-  // this thread's word of scratch vector `id`, pair k
-  auto vec = [&](int id) -> double2* { return (id < n_smem ? sm : ws) + (size_t)id * VS + lane; };
   const int tail = vid_tail(a.max_treedepth);
 
-  for (int chain = slot; chain < a.n_chains; chain += n_slots) {
-    double2 q[NP], p[NP], g[NP], var[NP];
-    load_row<G, NP>(a.q + (size_t)chain * a.ld, lane, ldh, q);
-    load_row<G, NP>(a.var + (size_t)chain * a.ld, lane, ldh, var);
-    mask_tail<G, NP>(lane, D, q);
-    mask_tail<G, NP>(lane, D, var);
-
-    double* const ad = a.adapt + (size_t)chain * LMC_ADAPT_STRIDE;
-    double log_step = ad[LMC_ADAPT_LOG_STEP], log_bar = ad[LMC_ADAPT_LOG_BAR], hbar = ad[LMC_ADAPT_HBAR];
-    double da_count = ad[LMC_ADAPT_COUNT];
-    const double da_mu = ad[LMC_ADAPT_MU];
-    double w_fg = ad[LMC_ADAPT_W_FG], w_bg = ad[LMC_ADAPT_W_BG];
-    long long n_samples = (long long)ad[LMC_ADAPT_NSAMPLES];
-    long long window = (long long)ad[LMC_ADAPT_WINDOW];
-    const uint64_t seed = (a.rng.mode == LMC_RNG_PHILOX) ? a.rng.seeds[chain] : 0ull;
+  for (;;) {
+    // ---- pop the next (chain, transition) unit ---------------------------------------------------------------------
+    int chain = -1, t = 0;
+    if (lane == 0) {
+      const unsigned h = atomicAdd(&sv.ctr[0], 1u);
+      if (h < total_units) {
+        volatile unsigned long long* e = sv.ring + (h % (unsigned)a.n_chains);
+        unsigned long long v = *e;
+        while ((unsigned)(v >> 32) != h + 1u) {  // only when the queue ran dry (fewer chains than groups, or the tail)
+          __nanosleep(100);
+          v = *e;
+        }
+        __threadfence();  // acquire: the previous owner's state writes are ordered before its push
+        chain = (int)(unsigned)v;  // bit 31 = dead flag
+        t = *(volatile int*)(sv.prog + (chain & 0x7fffffff));
+      }
+      if constexpr (G > 32) {
+        s_pop[0] = chain;
+        s_pop[1] = t;
+      }
+    }
+    if constexpr (G == 32) {
+      chain = __shfl_sync(0xffffffffu, chain, 0);
+      t = __shfl_sync(0xffffffffu, t, 0);
+    } else {
+      __syncthreads();
+      chain = s_pop[0];
+      t = s_pop[1];
+    }
+    if (chain == -1) break;
+    bool dead = ((unsigned)chain & kDeadBit) != 0u;
+    chain &= 0x7fffffff;
+    const size_t row = (size_t)chain * a.n_trans + t;
+    double* const srow = a.stats + row * LMC_NSTATS;
+    double* const trow = a.trace + (size_t)chain * a.trace_chain_stride + (size_t)t * a.trace_draw_stride;
     int status = 0;
 
-    for (int t = 0; t < a.n_trans; ++t) {
+    if (!dead) {
+      // chain state lives in HBM between transitions and may have been written by another SM: bypass L1 (ld.cg)
+      double2 q[NP], p[NP], g[NP], var[NP];
+      load_row_cg<G, NP>(a.q + (size_t)chain * a.ld, lane, ldh, q);
+      load_row_cg<G, NP>(a.var + (size_t)chain * a.ld, lane, ldh, var);
+      mask_tail<G, NP>(lane, D, q);
+      mask_tail<G, NP>(lane, D, var);
+
+      double* const ad = a.adapt + (size_t)chain * LMC_ADAPT_STRIDE;
+      DualAvg da{__ldcg(ad + LMC_ADAPT_LOG_STEP), __ldcg(ad + LMC_ADAPT_LOG_BAR), __ldcg(ad + LMC_ADAPT_HBAR),
+                 __ldcg(ad + LMC_ADAPT_COUNT), __ldcg(ad + LMC_ADAPT_MU)};
+      WelfordScalars wel{__ldcg(ad + LMC_ADAPT_W_FG), __ldcg(ad + LMC_ADAPT_W_BG),
+                         (long long)__ldcg(ad + LMC_ADAPT_NSAMPLES), (long long)__ldcg(ad + LMC_ADAPT_WINDOW)};
+      const uint64_t seed = (a.rng.mode == LMC_RNG_PHILOX) ? a.rng.seeds[chain] : 0ull;
+
       const long long it = a.iter0 + t;  // BaseHMC.iter_count
       const bool tune = it < a.n_tune;
       const bool adapt_step = tune && a.adapt_step_size;  // base_hmc.py:151
       unsigned uc = 0;                                    // uniforms consumed by this transition
-      const size_t row = (size_t)chain * a.n_trans + t;
+      double u_lane = 0.0;  // PHILOX: uniform number (uc & ~31) + (lane & 31) of this transition, refilled every 32
       auto next_uniform = [&]() -> double {
         double u;
         if (a.rng.mode == LMC_RNG_TAPE) {
@@ -130,403 +190,150 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
             status |= LMC_STATUS_TAPE_EXHAUSTED;
           }
         } else {
-          u = philox_uniform(seed, it, uc);
+          // one Philox block per lane yields the next 32 uniforms of the stream; they are handed out by shuffle
+          if ((uc & 31u) == 0u) u_lane = philox_uniform(seed, it, uc + (unsigned)(lane & 31));
+          u = __shfl_sync(0xffffffffu, u_lane, (int)(uc & 31u));
         }
         ++uc;
         return u;
       };
 
       // ---- p0 = potential.random()  (quadpotential.py:221-224 / 374-376) ---------------------------------------
-#pragma unroll
-      for (int k = 0; k < NP; ++k) {
-        const int j = lane + k * G;
-        double2 n = make_double2(0.0, 0.0);
-        if (a.rng.mode == LMC_RNG_TAPE) {
-          const double* nr = a.rng.normals + row * D;
-          if (2 * j < D) n.x = nr[2 * j];
-          if (2 * j + 1 < D) n.y = nr[2 * j + 1];
-        } else if (2 * j < D) {
-          n = philox_normal_pair(seed, it, (uint32_t)j);
-        }
-        // inv_stds * vals with inv_stds = 1/sqrt(var): IEEE sqrt and divide, identical to the stored arrays
-        p[k].x = (2 * j < D) ? mul_rn(1.0 / sqrt(var[k].x), n.x) : 0.0;
-        p[k].y = (2 * j + 1 < D) ? mul_rn(1.0 / sqrt(var[k].y), n.y) : 0.0;
-      }
+      draw_momentum<G, NP>(lane, D, a.rng.mode == LMC_RNG_TAPE ? a.rng.normals + row * D : nullptr, seed, it, var, p);
 
       // ---- start = integrator.compute_state(q0, p0)  (integration.py:52-66) -------------------------------------
       double E0, logp0;
       eval_energy<false>(tgt, grp, D, ldh, q, p, g, var, 0.0, E0, logp0);
-      double* const srow = a.stats + row * LMC_NSTATS;
-      if (!isfinite(E0)) {  // base_hmc.py:145-148: the reference raises; we flag the chain and stop it
+      if (!isfinite(E0)) {  // base_hmc.py:145-148: the reference raises; we flag the chain and stop it (rows -> NaN)
         status |= LMC_STATUS_BAD_INITIAL_ENERGY;
-        const double nan = CUDART_NAN;
-        for (int tt = t; tt < a.n_trans; ++tt) {
-          double* tr = a.trace + (size_t)chain * a.trace_chain_stride + (size_t)tt * a.trace_draw_stride;
-          for (int e = lane; e < D; e += G) tr[e] = nan;
-          if (lane == 0) {
-            double* s2 = a.stats + ((size_t)chain * a.n_trans + tt) * LMC_NSTATS;
-            for (int s = 0; s < LMC_NSTATS; ++s) s2[s] = nan;
-          }
-        }
-        break;
-      }
-      const double eps = exp(adapt_step ? log_step : log_bar);  // step_sizes.py:58-69
+        dead = true;
+      } else {
+        const double eps = exp(adapt_step ? da.log_step : da.log_bar);  // step_sizes.py:58-69
 
-      double accept_stat, stat_a, stat_b, stat_energy, stat_energy_error, stat_c, stat_logp;
-      bool diverging = false;
+        double accept_stat, stat_a, stat_b, stat_energy, stat_energy_error, stat_c, stat_logp;
+        bool diverging = false;
 
-      if constexpr (KIND == KIND_NUTS) {
-        // ---- NUTS._hamiltonian_step + _Tree  (nuts.py:204-224, 251-435) -----------------------------------------
-        const int max_depth = (tune && it < 200) ? a.early_max_treedepth : a.max_treedepth;  // nuts.py:205-208
-        // trajectory state (nuts.py:267-282)
-        XF Wp = xf_zero();  // exp(log_size) - 1: total weight of the accepted subtrees (the start point has weight 1)
-        XF Acc = xf_zero(); // exp(log_weighted_accept_sum)
-        double max_dE = 0.0;
-        double prop_E = E0, prop_logp = logp0;
-        int depth = 0;
-        long long n_prop = 0;
-        bool turning = false;
-        int reg_edge = 0;  // which trajectory edge (q,p,g) currently sits in registers: 0 both (start), +1 R, -1 L
+        if constexpr (KIND == KIND_NUTS) {
+          // ---- NUTS._hamiltonian_step + _Tree  (nuts.py:204-224, 251-435) ---------------------------------------
+          const int max_depth = (tune && it < 200) ? a.early_max_treedepth : a.max_treedepth;  // nuts.py:205-208
+          TrajScalars tr{xf_zero(), xf_zero(), 0.0, E0, logp0, 0, 0};
+          int reg_edge = 0;  // which trajectory edge (q,p,g) currently sits in registers: 0 both (start), +1 R, -1 L
+          tree_init<G, NP>(sc, tail, q, p, g);
+          for (int d = 0; d < max_depth; ++d) {  // nuts.py:212
+            // logbern(log 0.5): log(u) < log(0.5) <=> u < 0.5 (log is monotone; the two can only disagree for the
+            // single double adjacent to 0.5)                                                          nuts.py:213
+            const int dir = (next_uniform() < 0.5) ? 1 : -1;
+            if (reg_edge != 0 && reg_edge != dir) {  // fetch the edge we extend from (nuts.py:297 / 306)
+              const int base = tail + (dir > 0 ? T_RQ : T_LQ);
 #pragma unroll
-        for (int k = 0; k < NP; ++k) {
-          vec(tail + T_LQ)[k * G] = q[k];
-          vec(tail + T_LP)[k * G] = p[k];
-          vec(tail + T_LG)[k * G] = g[k];
-          vec(tail + T_RQ)[k * G] = q[k];
-          vec(tail + T_RP)[k * G] = p[k];
-          vec(tail + T_RG)[k * G] = g[k];
-          vec(tail + T_PSUM)[k * G] = p[k];   // p_sum = start.p.copy()
-          vec(tail + T_PROPQ)[k * G] = q[k];  // proposal = start
-        }
-        for (int d = 0; d < max_depth; ++d) {  // nuts.py:212
-          // logbern(log 0.5): log(u) < log(0.5) <=> u < 0.5 (log is monotone; the two can only disagree for the single
-          // double adjacent to 0.5)                                                                   nuts.py:213
-          const int dir = (next_uniform() < 0.5) ? 1 : -1;
-          if (reg_edge != 0 && reg_edge != dir) {  // fetch the edge we extend from (nuts.py:297 / 306)
-            const int base = tail + (dir > 0 ? T_RQ : T_LQ);
-#pragma unroll
-            for (int k = 0; k < NP; ++k) {
-              q[k] = vec(base + 0)[k * G];
-              p[k] = vec(base + 1)[k * G];
-              g[k] = vec(base + 2)[k * G];
+              for (int k = 0; k < NP; ++k) {
+                q[k] = sc.vec(base + 0)[k * G];
+                p[k] = sc.vec(base + 1)[k * G];
+                g[k] = sc.vec(base + 2)[k * G];
+              }
             }
-          }
-          const double eps_d = dir > 0 ? eps : -eps;
-          unsigned free_slots = 0xffffffffu;  // proposal-slot pool: bit s set = slot s free
-          int fail = 0;                       // 1 = diverging, 2 = turning
-          long long n_leaves = 0;
-          // summary of the subtree being assembled on top of the stack ("cur"); its right edge is always z
-          double2 cur_lp[NP], cur_ps[NP];
-          XF cur_w = xf_zero(), cur_a = xf_zero();  // exp(log_size), exp(log_weighted_accept_sum) of "cur"
-          double cur_pE = 0.0, cur_plogp = 0.0;
-          int cur_pslot = kLeafProp;
+            const double eps_d = dir > 0 ? eps : -eps;
+            unsigned free_slots = 0xffffffffu;  // proposal-slot pool: bit s set = slot s free
+            int fail = 0;                       // 1 = diverging, 2 = turning
+            long long n_leaves = 0;
+            double2 cur_lp[NP], cur_ps[NP];
+            CurTree cur{xf_zero(), xf_zero(), 0.0, 0.0, kLeafProp};
 
-          const unsigned n_leaf_total = 1u << d;
-          for (unsigned i = 0; i < n_leaf_total; ++i) {  // leaves of _build_subtree in integration order
-            double E, logp;
-            leapfrog(tgt, grp, D, ldh, eps_d, q, p, g, var, E, logp);  // nuts.py:347
-            double dE = E - E0;                                        // :352
-            if (isnan(dE)) dE = CUDART_INF;                            // :353-354
-            if (fabs(dE) > fabs(max_dE)) max_dE = dE;                  // :356-357
-            ++n_leaves;
-            if (!(fabs(dE) < a.Emax)) {  // :358 / :370-375
-              fail = 1;
-              break;
-            }
-            cur_w = xf_exp(-dE);                             // log_size = -dE
-            cur_a = (-dE < 0.0) ? xf_sqr(cur_w) : cur_w;     // log_p_accept_weighted = -dE + min(0, -dE)  (:363)
-            cur_pE = E;
-            cur_plogp = logp;
-            cur_pslot = kLeafProp;
-#pragma unroll
-            for (int k = 0; k < NP; ++k) cur_lp[k] = cur_ps[k] = p[k];
-
-            unsigned jbits = i;
-            int lvl = 0;
-            while (jbits & 1u) {  // merge with the stack entry of this level (nuts.py:387-417)
-              double2 t1_lp[NP], t1_rp[NP], t1_ps[NP];
-              if (lvl == 0) {
-#pragma unroll
-                for (int k = 0; k < NP; ++k) t1_lp[k] = t1_rp[k] = t1_ps[k] = vec(vid_stack(0, 0))[k * G];
-              } else {
-#pragma unroll
-                for (int k = 0; k < NP; ++k) {
-                  t1_lp[k] = vec(vid_stack(lvl, 0))[k * G];
-                  t1_rp[k] = vec(vid_stack(lvl, 1))[k * G];
-                  t1_ps[k] = vec(vid_stack(lvl, 2))[k * G];
-                }
-              }
-              double dots[6] = {0.0, 0.0, 1.0, 1.0, 1.0, 1.0};
-              if (lvl == 0) {
-                double d2[2] = {0.0, 0.0};
-#pragma unroll
-                for (int k = 0; k < NP; ++k) {
-                  const double2 ps = add2(t1_ps[k], cur_ps[k]);  // p_sum = tree1.p_sum + tree2.p_sum (:390)
-                  d2[0] = dot2(d2[0], ps, mul2(var[k], t1_lp[k]));   // p_sum . left.v
-                  d2[1] = dot2(d2[1], ps, mul2(var[k], p[k]));       // p_sum . right.v
-                  cur_ps[k] = ps;
-                }
-                grp.allreduce(d2);
-                dots[0] = d2[0];
-                dots[1] = d2[1];
-              } else {
-                double d6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-                for (int k = 0; k < NP; ++k) {
-                  const double2 ps = add2(t1_ps[k], cur_ps[k]);    // :390
-                  const double2 ps1 = add2(t1_ps[k], cur_lp[k]);   // tree1.p_sum + tree2.left.p (:394)
-                  const double2 ps2 = add2(t1_rp[k], cur_ps[k]);   // tree1.right.p + tree2.p_sum (:396)
-                  const double2 v1l = mul2(var[k], t1_lp[k]), v1r = mul2(var[k], t1_rp[k]);
-                  const double2 v2l = mul2(var[k], cur_lp[k]), v2r = mul2(var[k], p[k]);
-                  d6[0] = dot2(d6[0], ps, v1l);
-                  d6[1] = dot2(d6[1], ps, v2r);
-                  d6[2] = dot2(d6[2], ps1, v1l);
-                  d6[3] = dot2(d6[3], ps1, v2l);
-                  d6[4] = dot2(d6[4], ps2, v1r);
-                  d6[5] = dot2(d6[5], ps2, v2r);
-                  cur_ps[k] = ps;
-                }
-                grp.allreduce(d6);
-#pragma unroll
-                for (int n = 0; n < 6; ++n) dots[n] = d6[n];
-              }
-#pragma unroll
-              for (int k = 0; k < NP; ++k) cur_lp[k] = t1_lp[k];  // left edge of the merged tree
-              const bool turn = (dots[0] <= 0) || (dots[1] <= 0) || (dots[2] <= 0) || (dots[3] <= 0) ||
-                                (dots[4] <= 0) || (dots[5] <= 0);  // :391-398 (dots 2..5 preset to 1 at level 0)
-              const XF nw = xf_add(XF{ss->wm[lvl], ss->we[lvl]}, cur_w);   // log_size = logaddexp(...)        (:400)
-              const XF na = xf_add(XF{ss->am[lvl], ss->ae[lvl]}, cur_a);   // log_weighted_accept_sum      (:401-403)
-              // logbern(tree2.log_size - log_size) <=> u * size < size2; the uniform is drawn even when turning (:404)
-              const int t1_pslot = ss->pslot[lvl];
-              if (xf_u_less(next_uniform(), nw, cur_w)) {
-                free_slots |= 1u << t1_pslot;  // keep tree2's proposal, drop tree1's
-              } else {
-                if (cur_pslot != kLeafProp) free_slots |= 1u << cur_pslot;
-                cur_pslot = t1_pslot;
-                cur_pE = ss->pE[lvl];
-                cur_plogp = ss->plogp[lvl];
-              }
-              cur_w = nw;
-              cur_a = na;
-              if (turn) {
-                fail = 2;
+            const unsigned n_leaf_total = 1u << d;
+            for (unsigned i = 0; i < n_leaf_total; ++i) {  // leaves of _build_subtree in integration order
+              double E, logp;
+              leapfrog(tgt, grp, D, ldh, eps_d, q, p, g, var, E, logp);  // nuts.py:347
+              ++n_leaves;
+              if (!leaf_init<NP>(E, logp, E0, a.Emax, p, tr.max_dE, cur, cur_lp, cur_ps)) {
+                fail = 1;
                 break;
               }
-              jbits >>= 1;
-              ++lvl;
-            }
-            if (fail) break;
-            if (i + 1 < n_leaf_total) {  // push "cur" at level lvl (the last leaf's result stays in registers)
-              if (cur_pslot == kLeafProp) {
-                cur_pslot = __ffs(free_slots) - 1;
-                free_slots &= ~(1u << cur_pslot);
-#pragma unroll
-                for (int k = 0; k < NP; ++k) vec(vid_prop(cur_pslot))[k * G] = q[k];
-              }
-              if (lvl == 0) {
-#pragma unroll
-                for (int k = 0; k < NP; ++k) vec(vid_stack(0, 0))[k * G] = p[k];
-              } else {
-#pragma unroll
-                for (int k = 0; k < NP; ++k) {
-                  vec(vid_stack(lvl, 0))[k * G] = cur_lp[k];
-                  vec(vid_stack(lvl, 1))[k * G] = p[k];
-                  vec(vid_stack(lvl, 2))[k * G] = cur_ps[k];
+              unsigned jbits = i;
+              int lvl = 0;
+              while (jbits & 1u) {  // merge with the stack entry of this level (nuts.py:387-417)
+                if (merge_level<G, NP>(sc, grp, ss, lvl, var, p, cur_lp, cur_ps, cur, free_slots, next_uniform())) {
+                  fail = 2;
+                  break;
                 }
+                jbits >>= 1;
+                ++lvl;
               }
-              // One writer.  Readers see it after at least one group barrier (the next leaf's energy reduction) and
-              // finished reading the previous occupant before the barrier that preceded this point.
-              if (lane == 0) {
-                ss->wm[lvl] = cur_w.m;
-                ss->we[lvl] = cur_w.e;
-                ss->am[lvl] = cur_a.m;
-                ss->ae[lvl] = cur_a.e;
-                ss->pE[lvl] = cur_pE;
-                ss->plogp[lvl] = cur_plogp;
-                ss->pslot[lvl] = cur_pslot;
+              if (fail) break;
+              if (i + 1 < n_leaf_total) {  // push "cur" at level lvl (the last leaf's result stays in registers)
+                // One writer.  Readers see it after at least one group barrier (the next leaf's energy reduction)
+                // and finished reading the previous occupant before the barrier that preceded this point.
+                push_cur<G, NP>(sc, ss, lvl, q, p, cur_lp, cur_ps, cur, free_slots);
+                if constexpr (G == 32) __syncwarp();
               }
-              if constexpr (G == 32) __syncwarp();
+            }
+            ++tr.depth;            // nuts.py:315
+            tr.n_prop += n_leaves;  // :316
+            if (fail) {            // :318-319 -> :216-217 (the subtree is discarded, no uniform is drawn)
+              diverging = (fail == 1);
+              break;
+            }
+            if (extend_top<G, NP>(sc, grp, tail, dir, var, q, p, cur_lp, cur_ps, cur, tr, next_uniform())) break;  // :340
+            if (d + 1 < max_depth) {  // self.right / self.left = tree.right (:304 / :313)
+              const int base = tail + (dir > 0 ? T_RQ : T_LQ);
+#pragma unroll
+              for (int k = 0; k < NP; ++k) {
+                sc.vec(base + 0)[k * G] = q[k];
+                sc.vec(base + 1)[k * G] = p[k];
+                sc.vec(base + 2)[k * G] = g[k];
+              }
+              reg_edge = dir;
             }
           }
-          ++depth;              // nuts.py:315
-          n_prop += n_leaves;   // :316
-          if (fail) {           // :318-319 -> :216-217 (the subtree is discarded, no uniform is drawn)
-            diverging = (fail == 1);
-            turning = (fail == 2);
-            break;
-          }
-          // ---- top of _Tree.extend (nuts.py:321-340): T = cur, T.left.p = cur_lp, T.right = z, T.p_sum = cur_ps
-          if (xf_u_less(next_uniform(), xf_add(Wp, xf_one()), cur_w)) {  // logbern(tree.log_size - self.log_size) :321-323
-            prop_E = cur_pE;
-            prop_logp = cur_plogp;
-            if (cur_pslot == kLeafProp) {
+          // _Tree.stats (nuts.py:419-435)
+          accept_stat = mean_tree_accept(tr);
+          stat_a = (double)tr.depth;
+          stat_b = (double)tr.n_prop;
+          stat_energy = tr.prop_E;
+          stat_energy_error = tr.prop_E - E0;
+          stat_c = tr.max_dE;
+          stat_logp = tr.prop_logp;
 #pragma unroll
-              for (int k = 0; k < NP; ++k) vec(tail + T_PROPQ)[k * G] = q[k];
-            } else {
+          for (int k = 0; k < NP; ++k) q[k] = sc.vec(tail + T_PROPQ)[k * G];  // hmc_step.end.q
+        } else {
+          // ---- HamiltonianMC._hamiltonian_step (hmc.py:140-182) -------------------------------------------------
+          double2 q0[NP];
 #pragma unroll
-              for (int k = 0; k < NP; ++k) vec(tail + T_PROPQ)[k * G] = vec(vid_prop(cur_pslot))[k * G];
-            }
-          }
-          Wp = xf_add(Wp, cur_w);    // log_size = logaddexp(log_size, tree.log_size)                     (:325)
-          Acc = xf_add(Acc, cur_a);  // log_weighted_accept_sum                                          (:326-328)
-          double d6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+          for (int k = 0; k < NP; ++k) q0[k] = q[k];
+          const double path_length = next_uniform() * a.path_length;  // :141
+          const int n_steps = hmc_n_steps(path_length, eps, a.max_steps);  // :142-143
+          double E = E0, logp = logp0;
+          for (int s = 0; s < n_steps; ++s) leapfrog(tgt, grp, D, ldh, eps, q, p, g, var, E, logp);  // :149-150
+          double dE;
+          diverging = hmc_energy_check(E0, E, a.Emax, dE, accept_stat);  // :154-164
+          bool accepted = false;
+          if (!diverging) accepted = !(next_uniform() >= accept_stat);  // :166 (no draw when diverging)
+          if (!accepted) {
 #pragma unroll
-          for (int k = 0; k < NP; ++k) {
-            const double2 psum = add2(vec(tail + T_PSUM)[k * G], cur_ps[k]);  // self.p_sum[:] += tree.p_sum (:329)
-            vec(tail + T_PSUM)[k * G] = psum;
-            const double2 oLp = vec(tail + T_LP)[k * G], oRp = vec(tail + T_RP)[k * G];  // old edges' momenta
-            const double2 voL = mul2(var[k], oLp), voR = mul2(var[k], oRp);
-            const double2 vTl = mul2(var[k], cur_lp[k]), vTr = mul2(var[k], p[k]);
-            if (dir > 0) {
-              // left = old left, right = T.right; leftmost = old trajectory with the ALIASED (already
-              // updated) p_sum, rightmost = T                                         (:300-303, :333-339)
-              const double2 ps1 = add2(psum, cur_lp[k]);   // leftmost_p_sum + rightmost_begin.p
-              const double2 ps2 = add2(oRp, cur_ps[k]);    // leftmost_end.p + rightmost_p_sum
-              d6[0] = dot2(d6[0], psum, voL);
-              d6[1] = dot2(d6[1], psum, vTr);
-              d6[2] = dot2(d6[2], ps1, voL);
-              d6[3] = dot2(d6[3], ps1, vTl);
-              d6[4] = dot2(d6[4], ps2, voR);
-              d6[5] = dot2(d6[5], ps2, vTr);
-            } else {
-              // left = T.right, right = old right; leftmost = T (begin = T.right, end = T.left), rightmost =
-              // old trajectory with the aliased p_sum                                  (:309-312, :333-339)
-              const double2 ps1 = add2(cur_ps[k], oLp);    // leftmost_p_sum + rightmost_begin.p
-              const double2 ps2 = add2(cur_lp[k], psum);   // leftmost_end.p + rightmost_p_sum
-              d6[0] = dot2(d6[0], psum, vTr);
-              d6[1] = dot2(d6[1], psum, voR);
-              d6[2] = dot2(d6[2], ps1, vTr);
-              d6[3] = dot2(d6[3], ps1, voL);
-              d6[4] = dot2(d6[4], ps2, vTl);
-              d6[5] = dot2(d6[5], ps2, voR);
-            }
+            for (int k = 0; k < NP; ++k) q[k] = q0[k];
           }
-          grp.allreduce(d6);
-          if ((d6[0] <= 0) || (d6[1] <= 0) || (d6[2] <= 0) || (d6[3] <= 0) || (d6[4] <= 0) || (d6[5] <= 0)) {
-            turning = true;  // :340
-            break;
-          }
-          if (d + 1 < max_depth) {  // self.right / self.left = tree.right (:304 / :313)
-            const int base = tail + (dir > 0 ? T_RQ : T_LQ);
-#pragma unroll
-            for (int k = 0; k < NP; ++k) {
-              vec(base + 0)[k * G] = q[k];
-              vec(base + 1)[k * G] = p[k];
-              vec(base + 2)[k * G] = g[k];
-            }
-            reg_edge = dir;
-          }
+          stat_a = (double)n_steps;
+          stat_b = path_length;
+          stat_energy = E;  // end-of-trajectory values even when rejected (:173-181)
+          stat_energy_error = dE;
+          stat_c = accepted ? 1.0 : 0.0;
+          stat_logp = logp;
         }
-        (void)turning;
-        // _Tree.stats (nuts.py:419-435)
-        double mta = 0.0;
-        // log_size > 0 <=> exp(log_size) - 1 > 0 in double; exp(lwas - logdiffexp(log_size, 0)) = Acc / (exp(log_size) - 1)
-        if (xf_value(Wp) > 0.0) mta = xf_ratio(Acc, Wp);
-        accept_stat = mta;
-        stat_a = (double)depth;
-        stat_b = (double)n_prop;
-        stat_energy = prop_E;
-        stat_energy_error = prop_E - E0;
-        stat_c = max_dE;
-        stat_logp = prop_logp;
-#pragma unroll
-        for (int k = 0; k < NP; ++k) q[k] = vec(tail + T_PROPQ)[k * G];  // hmc_step.end.q
-      } else {
-        // ---- HamiltonianMC._hamiltonian_step (hmc.py:140-182) ---------------------------------------------------
-        double2 q0[NP];
-#pragma unroll
-        for (int k = 0; k < NP; ++k) q0[k] = q[k];
-        const double path_length = next_uniform() * a.path_length;  // :141
-        const double ratio = path_length / eps;
-        int n_steps = ratio >= (double)a.max_steps ? a.max_steps : (int)ratio;  // :142-143 (int() truncates)
-        if (n_steps < 1) n_steps = 1;
-        double E = E0, logp = logp0;
-        for (int s = 0; s < n_steps; ++s) leapfrog(tgt, grp, D, ldh, eps, q, p, g, var, E, logp);  // :149-150
-        if (!isfinite(E)) diverging = true;       // :154-155
-        double dE = E0 - E;                        // :156
-        if (isnan(dE)) dE = -CUDART_INF;           // :157-158
-        if (fabs(dE) > a.Emax) diverging = true;   // :159-162
-        accept_stat = fmin(1.0, exp(dE));          // :164
-        bool accepted = false;
-        if (!diverging) accepted = !(next_uniform() >= accept_stat);  // :166 (no draw when diverging)
-        if (!accepted) {
-#pragma unroll
-          for (int k = 0; k < NP; ++k) q[k] = q0[k];
-        }
-        stat_a = (double)n_steps;
-        stat_b = path_length;
-        stat_energy = E;  // end-of-trajectory values even when rejected (:173-181)
-        stat_energy_error = dE;
-        stat_c = accepted ? 1.0 : 0.0;
-        stat_logp = logp;
-      }
 
-      // ---- step_adapt.update(accept_stat, adapt_step)  (step_sizes.py:71-92) -----------------------------------
-      if (adapt_step) {
-        const double w = 1.0 / (da_count + a.t0);
-        hbar = (1.0 - w) * hbar + w * (a.target_accept - accept_stat);
-        log_step = da_mu - hbar * sqrt(da_count) / a.gamma;
-        const double mk = pow(da_count, -a.k);
-        log_bar = mk * log_step + (1.0 - mk) * log_bar;
-        da_count += 1.0;
-      }
-      // ---- potential.update(end.q, end.q_grad, tune)  (quadpotential.py:231-245, 322-338) ----------------------
-      if (tune && a.adapt_mass) {
-        const size_t off = (size_t)chain * a.ld;
-        double2* mfg = reinterpret_cast<double2*>(a.mean_fg + off);
-        double2* rfg = reinterpret_cast<double2*>(a.rawvar_fg + off);
-        double2* mbg = reinterpret_cast<double2*>(a.mean_bg + off);
-        double2* rbg = reinterpret_cast<double2*>(a.rawvar_bg + off);
-        w_fg += 1.0;
-        w_bg += 1.0;
-        const double prop_fg = 1.0 / w_fg, prop_bg = 1.0 / w_bg;
-        const bool sw = n_samples > 0 && window > 0 && (n_samples % window) == 0;
+        // ---- step_adapt.update(accept_stat, adapt_step)  (step_sizes.py:71-92) ---------------------------------
+        if (adapt_step) dual_average_update(da, accept_stat, a.target_accept, a.gamma, a.k, a.t0);
+        // ---- potential.update(end.q, end.q_grad, tune)  (quadpotential.py:231-245, 322-338) --------------------
+        if (tune && a.adapt_mass) {
+          const size_t off = (size_t)chain * a.ld;
+          welford_update<G, NP>(lane, D, ldh, a.mean_fg + off, a.rawvar_fg + off, a.mean_bg + off, a.rawvar_bg + off, q,
+                                var, wel, a.window_multiplier);
+        }
+
+        // ---- outputs: trace[:, i] = q (sampling.py:513) and the stats dict (base_hmc.py:185-188) ----------------
 #pragma unroll
         for (int k = 0; k < NP; ++k) {
           const int j = lane + k * G;
-          if (j < ldh) {
-            double2 m = mfg[j], r = rfg[j];
-            double2 od = make_double2(add_rn(q[k].x, -m.x), add_rn(q[k].y, -m.y));   // old_diff = x - mean
-            m = axpy2(m, prop_fg, od);                                               // mean += prop * old_diff
-            double2 nd = make_double2(add_rn(q[k].x, -m.x), add_rn(q[k].y, -m.y));   // new_diff = x - mean
-            r = add2(r, mul2(od, nd));                                               // raw_var += old*new
-            double2 m2 = mbg[j], r2 = rbg[j];
-            od = make_double2(add_rn(q[k].x, -m2.x), add_rn(q[k].y, -m2.y));
-            m2 = axpy2(m2, prop_bg, od);
-            nd = make_double2(add_rn(q[k].x, -m2.x), add_rn(q[k].y, -m2.y));
-            r2 = add2(r2, mul2(od, nd));
-            var[k] = make_double2(r.x / w_fg, r.y / w_fg);  // _update_from_weightvar(foreground) (:226-229)
-            if (2 * j >= D) var[k].x = 0.0;
-            if (2 * j + 1 >= D) var[k].y = 0.0;
-            if (sw) {  // foreground <- background, background <- fresh (:240-243)
-              mfg[j] = m2;
-              rfg[j] = r2;
-              mbg[j] = make_double2(0.0, 0.0);
-              rbg[j] = make_double2(0.0, 0.0);
-            } else {
-              mfg[j] = m;
-              rfg[j] = r;
-              mbg[j] = m2;
-              rbg[j] = r2;
-            }
-          }
-        }
-        if (sw) {
-          w_fg = w_bg;
-          w_bg = 0.0;
-          window = (long long)((double)window * a.window_multiplier);
-        }
-        ++n_samples;
-      }
-
-      // ---- outputs: trace[:, i] = q (sampling.py:513) and the stats dict (base_hmc.py:185-188) ------------------
-      {
-        double* tr = a.trace + (size_t)chain * a.trace_chain_stride + (size_t)t * a.trace_draw_stride;
-#pragma unroll
-        for (int k = 0; k < NP; ++k) {
-          const int j = lane + k * G;
-          if (2 * j < D) tr[2 * j] = q[k].x;
-          if (2 * j + 1 < D) tr[2 * j + 1] = q[k].y;
+          if (2 * j < D) trow[2 * j] = q[k].x;
+          if (2 * j + 1 < D) trow[2 * j + 1] = q[k].y;
         }
         if (lane == 0) {
           srow[LMC_STAT_DEPTH] = stat_a;
@@ -538,26 +345,43 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
           srow[LMC_STAT_MODEL_LOGP] = stat_logp;
           srow[LMC_STAT_DIVERGING] = diverging ? 1.0 : 0.0;
           srow[LMC_STAT_TUNE] = tune ? 1.0 : 0.0;
-          srow[LMC_STAT_STEP_SIZE] = exp(log_step);
-          srow[LMC_STAT_STEP_SIZE_BAR] = exp(log_bar);
+          srow[LMC_STAT_STEP_SIZE] = exp(da.log_step);
+          srow[LMC_STAT_STEP_SIZE_BAR] = exp(da.log_bar);
           srow[LMC_STAT_N_UNIFORMS] = (double)uc;
         }
-      }
+
+        // ---- write the chain's state back (its next transition may run on another SM) ---------------------------
+        store_row<G, NP>(a.q + (size_t)chain * a.ld, lane, ldh, q);
+        store_row<G, NP>(a.var + (size_t)chain * a.ld, lane, ldh, var);
+        if (lane == 0) {
+          ad[LMC_ADAPT_LOG_STEP] = da.log_step;
+          ad[LMC_ADAPT_LOG_BAR] = da.log_bar;
+          ad[LMC_ADAPT_HBAR] = da.hbar;
+          ad[LMC_ADAPT_COUNT] = da.count;
+          ad[LMC_ADAPT_W_FG] = wel.w_fg;
+          ad[LMC_ADAPT_W_BG] = wel.w_bg;
+          ad[LMC_ADAPT_NSAMPLES] = (double)wel.n_samples;
+          ad[LMC_ADAPT_WINDOW] = (double)wel.window;
+        }
+      }  // finite initial energy
+      if (lane == 0 && status) atomicOr(a.status + chain, status);
+    }  // !dead
+    if (dead) {  // a stopped chain: its remaining rows are NaN
+      const double nan = CUDART_NAN;
+      for (int e = lane; e < D; e += G) trow[e] = nan;
+      if (lane == 0)
+        for (int s = 0; s < LMC_NSTATS; ++s) srow[s] = nan;
     }
 
-    // ---- write the chain's state back ---------------------------------------------------------------------------
-    store_row<G, NP>(a.q + (size_t)chain * a.ld, lane, ldh, q);
-    store_row<G, NP>(a.var + (size_t)chain * a.ld, lane, ldh, var);
-    if (lane == 0) {
-      ad[LMC_ADAPT_LOG_STEP] = log_step;
-      ad[LMC_ADAPT_LOG_BAR] = log_bar;
-      ad[LMC_ADAPT_HBAR] = hbar;
-      ad[LMC_ADAPT_COUNT] = da_count;
-      ad[LMC_ADAPT_W_FG] = w_fg;
-      ad[LMC_ADAPT_W_BG] = w_bg;
-      ad[LMC_ADAPT_NSAMPLES] = (double)n_samples;
-      ad[LMC_ADAPT_WINDOW] = (double)window;
-      if (status) atomicOr(a.status + chain, status);
+    // ---- push the chain back for its next transition ---------------------------------------------------------------
+    __threadfence();  // release: this thread's state writes become visible before the push below
+    group_barrier<G>();
+    if (lane == 0 && t + 1 < a.n_trans) {
+      sv.prog[chain] = t + 1;
+      __threadfence();
+      const unsigned tk = atomicAdd(&sv.ctr[1], 1u);
+      *(volatile unsigned long long*)(sv.ring + (tk % (unsigned)a.n_chains)) =
+          ((unsigned long long)(tk + 1u) << 32) | (dead ? kDeadBit : 0u) | (unsigned)chain;
     }
   }
 }
@@ -622,12 +446,14 @@ int launch(const lmc_sampler_args& a, const Target& tgt) {
   if (occ < 1) return LMC_ERR_UNSUPPORTED;
 
   long long blocks_needed = ((long long)a.n_chains + CPB - 1) / CPB;
-  long long grid = (long long)n_sm * occ;
+  long long grid = (long long)n_sm * occ;  // persistent: every CTA is resident, so a group waiting on the ring never deadlocks
   if (a.tune_max_slots > 0 && grid * CPB > a.tune_max_slots) grid = (a.tune_max_slots + CPB - 1) / CPB;
   if (grid > blocks_needed) grid = blocks_needed;
   if (grid < 1) grid = 1;
-  const long long need = grid * CPB * (long long)cfg.ws_vecs * (long long)vec_bytes;
+  const long long need = (long long)sched_bytes(a.n_chains) + grid * CPB * (long long)cfg.ws_vecs * (long long)vec_bytes;
   if (need > a.workspace_bytes) return LMC_ERR_WORKSPACE;
+  if ((long long)a.n_chains * a.n_trans >= (1ll << 31)) return LMC_ERR_UNSUPPORTED;  // 32-bit scheduler tickets
+  sched_init_kernel<<<(a.n_chains + 255) / 256, 256, 0, (cudaStream_t)a.stream>>>(a.workspace, a.n_chains);
   kern<<<(unsigned)grid, BLOCK, smem, (cudaStream_t)a.stream>>>(a, tgt, cfg);
   LMC_CUDA(cudaGetLastError());
   return LMC_OK;

@@ -1,0 +1,378 @@
+// NUTS tree bookkeeping shared by the fused sampler kernel (lmc_sampler.cuh) and the callback-mode state machine
+// (lmc_callback.cu): the pieces of reference nuts.py:284-435 that sit between two leapfrog steps.
+//
+// The recursive _build_subtree (nuts.py:377-417) is run as the iterative binary-counter stack of SURVEY.md A.1: leaf i
+// is merged with stack level 0, 1, .. for every trailing 1-bit of i, which visits the merges in the post-order of the
+// reference's recursion, so uniforms are consumed in the same order.  A stack entry keeps left.p, right.p, p_sum
+// (velocities are recomputed as var*p, bit-identical to the stored ones) and an index into a small pool of
+// proposal-position vectors, so choosing a proposal moves an index, never a vector.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "lmc_device.cuh"
+
+namespace lmc {
+
+constexpr int kLeafProp = -1;  // "the proposal is the current leaf, still in registers"
+
+// scratch-vector ids (ordered hottest first; ids < n_smem_vecs are shared-memory resident in the fused kernel)
+//   0                 stack level 0: p  (left.p == right.p == p_sum for a single leaf)
+//   1, 2              proposal slots 0, 1
+//   3+4(l-1)+{0,1,2}  stack level l >= 1: left.p, right.p, p_sum
+//   3+4(l-1)+3        proposal slot l+1
+//   tail              trajectory edges L(q,p,g), R(q,p,g), trajectory p_sum, trajectory proposal q
+__host__ __device__ constexpr int vid_stack(int level, int which) { return level == 0 ? 0 : 3 + 4 * (level - 1) + which; }
+__host__ __device__ constexpr int vid_prop(int slot) { return slot < 2 ? 1 + slot : 4 * slot - 2; }
+__host__ __device__ constexpr int vid_tail(int max_depth) { return max_depth < 1 ? 3 : 4 * max_depth - 1; }
+enum { T_LQ = 0, T_LP, T_LG, T_RQ, T_RP, T_RG, T_PSUM, T_PROPQ, T_COUNT };
+__host__ __device__ constexpr int ws_vecs_nuts(int max_depth) { return vid_tail(max_depth) + T_COUNT; }
+
+// per-level scalars of the subtree stack (written by lane 0 only; every read is separated from the write by a group
+// barrier / __syncwarp or by a kernel boundary)
+struct StackScalars {
+  double wm[kMaxDepth], am[kMaxDepth];     // mantissas of exp(log_size), exp(log_weighted_accept_sum)
+  double pE[kMaxDepth], plogp[kMaxDepth];  // proposal energy / model_logp
+  int we[kMaxDepth], ae[kMaxDepth];        // exponents
+  int pslot[kMaxDepth];                    // proposal slot
+  int pad[kMaxDepth];
+};
+
+// Where a group's scratch vectors live.  Vector `id` occupies VS = G*NP pairs; this thread owns words lane + k*G.
+template <int G, int NP>
+struct Scratch {
+  double2* sm;  // shared-memory part (ids < n_smem), may be null when n_smem == 0
+  double2* ws;  // global part (ids are absolute: the first n_smem slots are unused there)
+  int n_smem;
+  int lane;
+  __device__ __forceinline__ double2* vec(int id) const {
+    return (id < n_smem ? sm : ws) + (size_t)id * (G * NP) + lane;
+  }
+};
+
+// summary of the subtree being assembled on top of the stack ("cur"); its right edge is always the current state z
+struct CurTree {
+  XF w, a;           // exp(log_size), exp(log_weighted_accept_sum)
+  double pE, plogp;  // proposal energy / model_logp
+  int pslot;         // proposal slot or kLeafProp
+};
+
+// trajectory-level scalars of _Tree (nuts.py:267-282)
+struct TrajScalars {
+  XF Wp;   // exp(log_size) - 1: total weight of the accepted subtrees (the start point has weight 1)
+  XF Acc;  // exp(log_weighted_accept_sum)
+  double max_dE, prop_E, prop_logp;
+  int depth;
+  long long n_prop;
+};
+
+// _Tree.__init__ (nuts.py:267-282): both edges and the proposal are the start state, p_sum = start.p.copy()
+template <int G, int NP>
+__device__ __forceinline__ void tree_init(const Scratch<G, NP>& sc, int tail, const double2 (&q)[NP],
+                                          const double2 (&p)[NP], const double2 (&g)[NP]) {
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    sc.vec(tail + T_LQ)[k * G] = q[k];
+    sc.vec(tail + T_LP)[k * G] = p[k];
+    sc.vec(tail + T_LG)[k * G] = g[k];
+    sc.vec(tail + T_RQ)[k * G] = q[k];
+    sc.vec(tail + T_RP)[k * G] = p[k];
+    sc.vec(tail + T_RG)[k * G] = g[k];
+    sc.vec(tail + T_PSUM)[k * G] = p[k];
+    sc.vec(tail + T_PROPQ)[k * G] = q[k];
+  }
+}
+
+// _single_step after the leapfrog (nuts.py:352-375).  Returns false when the leaf diverges.
+template <int NP>
+__device__ __forceinline__ bool leaf_init(double E, double logp, double E0, double Emax, const double2 (&p)[NP],
+                                          double& max_dE, CurTree& cur, double2 (&cur_lp)[NP], double2 (&cur_ps)[NP]) {
+  double dE = E - E0;                         // :352
+  if (isnan(dE)) dE = CUDART_INF;             // :353-354
+  if (fabs(dE) > fabs(max_dE)) max_dE = dE;   // :356-357
+  if (!(fabs(dE) < Emax)) return false;       // :358 / :370-375
+  cur.w = xf_exp(-dE);                                 // log_size = -dE
+  cur.a = (-dE < 0.0) ? xf_sqr(cur.w) : cur.w;         // log_p_accept_weighted = -dE + min(0, -dE)  (:363)
+  cur.pE = E;
+  cur.plogp = logp;
+  cur.pslot = kLeafProp;
+#pragma unroll
+  for (int k = 0; k < NP; ++k) cur_lp[k] = cur_ps[k] = p[k];
+  return true;
+}
+
+// One merge of _build_subtree (nuts.py:387-417): tree1 = stack entry `lvl`, tree2 = cur (right edge momentum p).
+// `u` is the uniform of logbern (:404), drawn by the caller even when the merged tree turns.  Returns `turning`.
+template <int G, int NP>
+__device__ __forceinline__ bool merge_level(const Scratch<G, NP>& sc, Group<G>& grp, const StackScalars* ss, int lvl,
+                                            const double2 (&var)[NP], const double2 (&p)[NP], double2 (&cur_lp)[NP],
+                                            double2 (&cur_ps)[NP], CurTree& cur, unsigned& free_slots, double u) {
+  double2 t1_lp[NP], t1_rp[NP], t1_ps[NP];
+  if (lvl == 0) {
+#pragma unroll
+    for (int k = 0; k < NP; ++k) t1_lp[k] = t1_rp[k] = t1_ps[k] = sc.vec(vid_stack(0, 0))[k * G];
+  } else {
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      t1_lp[k] = sc.vec(vid_stack(lvl, 0))[k * G];
+      t1_rp[k] = sc.vec(vid_stack(lvl, 1))[k * G];
+      t1_ps[k] = sc.vec(vid_stack(lvl, 2))[k * G];
+    }
+  }
+  bool turn;
+  if (lvl == 0) {
+    double d2[2] = {0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      const double2 ps = add2(t1_ps[k], cur_ps[k]);     // p_sum = tree1.p_sum + tree2.p_sum (:390)
+      d2[0] = dot2(d2[0], ps, mul2(var[k], t1_lp[k]));  // p_sum . left.v
+      d2[1] = dot2(d2[1], ps, mul2(var[k], p[k]));      // p_sum . right.v
+      cur_ps[k] = ps;
+    }
+    grp.allreduce(d2);
+    turn = (d2[0] <= 0) || (d2[1] <= 0);  // :391
+  } else {
+    double d6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      const double2 ps = add2(t1_ps[k], cur_ps[k]);   // :390
+      const double2 ps1 = add2(t1_ps[k], cur_lp[k]);  // tree1.p_sum + tree2.left.p (:394)
+      const double2 ps2 = add2(t1_rp[k], cur_ps[k]);  // tree1.right.p + tree2.p_sum (:396)
+      const double2 v1l = mul2(var[k], t1_lp[k]), v1r = mul2(var[k], t1_rp[k]);
+      const double2 v2l = mul2(var[k], cur_lp[k]), v2r = mul2(var[k], p[k]);
+      d6[0] = dot2(d6[0], ps, v1l);
+      d6[1] = dot2(d6[1], ps, v2r);
+      d6[2] = dot2(d6[2], ps1, v1l);
+      d6[3] = dot2(d6[3], ps1, v2l);
+      d6[4] = dot2(d6[4], ps2, v1r);
+      d6[5] = dot2(d6[5], ps2, v2r);
+      cur_ps[k] = ps;
+    }
+    grp.allreduce(d6);
+    turn = (d6[0] <= 0) || (d6[1] <= 0) || (d6[2] <= 0) || (d6[3] <= 0) || (d6[4] <= 0) || (d6[5] <= 0);  // :391-398
+  }
+#pragma unroll
+  for (int k = 0; k < NP; ++k) cur_lp[k] = t1_lp[k];  // left edge of the merged tree
+  const XF nw = xf_add(XF{ss->wm[lvl], ss->we[lvl]}, cur.w);  // log_size = logaddexp(...)             (:400)
+  const XF na = xf_add(XF{ss->am[lvl], ss->ae[lvl]}, cur.a);  // log_weighted_accept_sum           (:401-403)
+  // logbern(tree2.log_size - log_size) <=> u * size < size2                                            (:404)
+  const int t1_pslot = ss->pslot[lvl];
+  if (xf_u_less(u, nw, cur.w)) {
+    free_slots |= 1u << t1_pslot;  // keep tree2's proposal, drop tree1's
+  } else {
+    if (cur.pslot != kLeafProp) free_slots |= 1u << cur.pslot;
+    cur.pslot = t1_pslot;
+    cur.pE = ss->pE[lvl];
+    cur.plogp = ss->plogp[lvl];
+  }
+  cur.w = nw;
+  cur.a = na;
+  return turn;
+}
+
+// Push "cur" (right edge state q, p) as stack entry `lvl`.  One writer for the scalars (lane 0).
+template <int G, int NP>
+__device__ __forceinline__ void push_cur(const Scratch<G, NP>& sc, StackScalars* ss, int lvl, const double2 (&q)[NP],
+                                         const double2 (&p)[NP], const double2 (&cur_lp)[NP],
+                                         const double2 (&cur_ps)[NP], CurTree& cur, unsigned& free_slots) {
+  if (cur.pslot == kLeafProp) {
+    cur.pslot = __ffs(free_slots) - 1;
+    free_slots &= ~(1u << cur.pslot);
+#pragma unroll
+    for (int k = 0; k < NP; ++k) sc.vec(vid_prop(cur.pslot))[k * G] = q[k];
+  }
+  if (lvl == 0) {
+#pragma unroll
+    for (int k = 0; k < NP; ++k) sc.vec(vid_stack(0, 0))[k * G] = p[k];
+  } else {
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      sc.vec(vid_stack(lvl, 0))[k * G] = cur_lp[k];
+      sc.vec(vid_stack(lvl, 1))[k * G] = p[k];
+      sc.vec(vid_stack(lvl, 2))[k * G] = cur_ps[k];
+    }
+  }
+  if (sc.lane == 0) {
+    ss->wm[lvl] = cur.w.m;
+    ss->we[lvl] = cur.w.e;
+    ss->am[lvl] = cur.a.m;
+    ss->ae[lvl] = cur.a.e;
+    ss->pE[lvl] = cur.pE;
+    ss->plogp[lvl] = cur.plogp;
+    ss->pslot[lvl] = cur.pslot;
+  }
+}
+
+// Top of _Tree.extend after a completed subtree T = cur (nuts.py:321-340): T.left.p = cur_lp, T.right = z = (q, p),
+// T.p_sum = cur_ps.  `u` is the uniform of the biased progressive accept (:321-323).  Returns `turning`.
+template <int G, int NP>
+__device__ __forceinline__ bool extend_top(const Scratch<G, NP>& sc, Group<G>& grp, int tail, int dir,
+                                           const double2 (&var)[NP], const double2 (&q)[NP], const double2 (&p)[NP],
+                                           const double2 (&cur_lp)[NP], const double2 (&cur_ps)[NP],
+                                           const CurTree& cur, TrajScalars& tr, double u) {
+  if (xf_u_less(u, xf_add(tr.Wp, xf_one()), cur.w)) {  // logbern(tree.log_size - self.log_size) :321-323
+    tr.prop_E = cur.pE;
+    tr.prop_logp = cur.plogp;
+    if (cur.pslot == kLeafProp) {
+#pragma unroll
+      for (int k = 0; k < NP; ++k) sc.vec(tail + T_PROPQ)[k * G] = q[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < NP; ++k) sc.vec(tail + T_PROPQ)[k * G] = sc.vec(vid_prop(cur.pslot))[k * G];
+    }
+  }
+  tr.Wp = xf_add(tr.Wp, cur.w);    // log_size = logaddexp(log_size, tree.log_size)                     (:325)
+  tr.Acc = xf_add(tr.Acc, cur.a);  // log_weighted_accept_sum                                          (:326-328)
+  double d6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    const double2 psum = add2(sc.vec(tail + T_PSUM)[k * G], cur_ps[k]);  // self.p_sum[:] += tree.p_sum (:329)
+    sc.vec(tail + T_PSUM)[k * G] = psum;
+    const double2 oLp = sc.vec(tail + T_LP)[k * G], oRp = sc.vec(tail + T_RP)[k * G];  // old edges' momenta
+    const double2 voL = mul2(var[k], oLp), voR = mul2(var[k], oRp);
+    const double2 vTl = mul2(var[k], cur_lp[k]), vTr = mul2(var[k], p[k]);
+    if (dir > 0) {
+      // left = old left, right = T.right; leftmost = old trajectory with the ALIASED (already updated) p_sum,
+      // rightmost = T                                                          (:300-303, :333-339)
+      const double2 ps1 = add2(psum, cur_lp[k]);  // leftmost_p_sum + rightmost_begin.p
+      const double2 ps2 = add2(oRp, cur_ps[k]);   // leftmost_end.p + rightmost_p_sum
+      d6[0] = dot2(d6[0], psum, voL);
+      d6[1] = dot2(d6[1], psum, vTr);
+      d6[2] = dot2(d6[2], ps1, voL);
+      d6[3] = dot2(d6[3], ps1, vTl);
+      d6[4] = dot2(d6[4], ps2, voR);
+      d6[5] = dot2(d6[5], ps2, vTr);
+    } else {
+      // left = T.right, right = old right; leftmost = T (begin = T.right, end = T.left), rightmost = old trajectory
+      // with the aliased p_sum                                                 (:309-312, :333-339)
+      const double2 ps1 = add2(cur_ps[k], oLp);   // leftmost_p_sum + rightmost_begin.p
+      const double2 ps2 = add2(cur_lp[k], psum);  // leftmost_end.p + rightmost_p_sum
+      d6[0] = dot2(d6[0], psum, vTr);
+      d6[1] = dot2(d6[1], psum, voR);
+      d6[2] = dot2(d6[2], ps1, vTr);
+      d6[3] = dot2(d6[3], ps1, voL);
+      d6[4] = dot2(d6[4], ps2, vTl);
+      d6[5] = dot2(d6[5], ps2, voR);
+    }
+  }
+  grp.allreduce(d6);
+  return (d6[0] <= 0) || (d6[1] <= 0) || (d6[2] <= 0) || (d6[3] <= 0) || (d6[4] <= 0) || (d6[5] <= 0);  // :333-340
+}
+
+// _Tree.stats: mean_tree_accept (nuts.py:419-425).  log_size > 0 <=> exp(log_size) - 1 > 0 in double;
+// exp(lwas - logdiffexp(log_size, 0)) = Acc / (exp(log_size) - 1)
+__device__ __forceinline__ double mean_tree_accept(const TrajScalars& tr) {
+  return xf_value(tr.Wp) > 0.0 ? xf_ratio(tr.Acc, tr.Wp) : 0.0;
+}
+
+// ---- HamiltonianMC._hamiltonian_step scalars (hmc.py:141-164) -----------------------------------------------------------
+// n_steps = max(1, int(path_length / step_size)); n_steps = min(max_steps, n_steps)   (:142-143, int() truncates)
+__device__ __forceinline__ int hmc_n_steps(double path_length, double eps, int max_steps) {
+  const double ratio = path_length / eps;
+  int n = ratio >= (double)max_steps ? max_steps : (int)ratio;
+  return n < 1 ? 1 : n;
+}
+// energy_change = start.energy - end.energy with the divergence rules of :154-162; accept_stat = min(1, exp(dE)) (:164).
+// Returns `diverging`.
+__device__ __forceinline__ bool hmc_energy_check(double E0, double E, double Emax, double& dE, double& accept_stat) {
+  bool diverging = !isfinite(E);          // :154-155
+  dE = E0 - E;                            // :156
+  if (isnan(dE)) dE = -CUDART_INF;        // :157-158
+  if (fabs(dE) > Emax) diverging = true;  // :159-162
+  accept_stat = fmin(1.0, exp(dE));       // :164
+  return diverging;
+}
+
+// ---- the two adaptations that close BaseHMC._astep (base_hmc.py:161-162) ---------------------------------------------
+struct DualAvg {
+  double log_step, log_bar, hbar, count, mu;
+};
+// DualAverageAdaptation.update (step_sizes.py:71-92)
+__device__ __forceinline__ void dual_average_update(DualAvg& s, double accept_stat, double target, double gamma,
+                                                    double k, double t0) {
+  const double w = 1.0 / (s.count + t0);
+  s.hbar = (1.0 - w) * s.hbar + w * (target - accept_stat);
+  s.log_step = s.mu - s.hbar * sqrt(s.count) / gamma;
+  const double mk = pow(s.count, -k);
+  s.log_bar = mk * s.log_step + (1.0 - mk) * s.log_bar;
+  s.count += 1.0;
+}
+
+struct WelfordScalars {
+  double w_fg, w_bg;
+  long long n_samples, window;
+};
+// QuadPotentialDiagAdapt.update (quadpotential.py:231-245) with _WeightedVariance.add_sample (:322-338) on both
+// estimators, the var refresh from the foreground (:226-229) and the window switch (:240-243).  Rows live in HBM and
+// may have been written by another SM (ld.cg).
+template <int G, int NP>
+__device__ __forceinline__ void welford_update(int lane, int D, int ldh, double* mean_fg, double* rawvar_fg,
+                                               double* mean_bg, double* rawvar_bg, const double2 (&q)[NP],
+                                               double2 (&var)[NP], WelfordScalars& ws, double window_multiplier) {
+  double2* mfg = reinterpret_cast<double2*>(mean_fg);
+  double2* rfg = reinterpret_cast<double2*>(rawvar_fg);
+  double2* mbg = reinterpret_cast<double2*>(mean_bg);
+  double2* rbg = reinterpret_cast<double2*>(rawvar_bg);
+  ws.w_fg += 1.0;
+  ws.w_bg += 1.0;
+  const double prop_fg = 1.0 / ws.w_fg, prop_bg = 1.0 / ws.w_bg;
+  const bool sw = ws.n_samples > 0 && ws.window > 0 && (ws.n_samples % ws.window) == 0;
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    const int j = lane + k * G;
+    if (j < ldh) {
+      double2 m = ldcg2(mfg + j), r = ldcg2(rfg + j);
+      double2 od = make_double2(add_rn(q[k].x, -m.x), add_rn(q[k].y, -m.y));  // old_diff = x - mean
+      m = axpy2(m, prop_fg, od);                                              // mean += prop * old_diff
+      double2 nd = make_double2(add_rn(q[k].x, -m.x), add_rn(q[k].y, -m.y));  // new_diff = x - mean
+      r = add2(r, mul2(od, nd));                                              // raw_var += old*new
+      double2 m2 = ldcg2(mbg + j), r2 = ldcg2(rbg + j);
+      od = make_double2(add_rn(q[k].x, -m2.x), add_rn(q[k].y, -m2.y));
+      m2 = axpy2(m2, prop_bg, od);
+      nd = make_double2(add_rn(q[k].x, -m2.x), add_rn(q[k].y, -m2.y));
+      r2 = add2(r2, mul2(od, nd));
+      var[k] = make_double2(r.x / ws.w_fg, r.y / ws.w_fg);  // _update_from_weightvar(foreground) (:226-229)
+      if (2 * j >= D) var[k].x = 0.0;
+      if (2 * j + 1 >= D) var[k].y = 0.0;
+      if (sw) {  // foreground <- background, background <- fresh (:240-243)
+        mfg[j] = m2;
+        rfg[j] = r2;
+        mbg[j] = make_double2(0.0, 0.0);
+        rbg[j] = make_double2(0.0, 0.0);
+      } else {
+        mfg[j] = m;
+        rfg[j] = r;
+        mbg[j] = m2;
+        rbg[j] = r2;
+      }
+    }
+  }
+  if (sw) {
+    ws.w_fg = ws.w_bg;
+    ws.w_bg = 0.0;
+    ws.window = (long long)((double)ws.window * window_multiplier);
+  }
+  ++ws.n_samples;
+}
+
+// p0 = potential.random() (quadpotential.py:221-224 / 374-376): inv_stds * normals, inv_stds = 1/sqrt(var) with IEEE
+// sqrt and divide, identical to the reference's stored arrays.  TAPE: `normals_row` = this transition's D normals.
+template <int G, int NP>
+__device__ __forceinline__ void draw_momentum(int lane, int D, const double* normals_row, uint64_t seed, long long it,
+                                              const double2 (&var)[NP], double2 (&p)[NP]) {
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    const int j = lane + k * G;
+    double2 n = make_double2(0.0, 0.0);
+    if (normals_row) {
+      if (2 * j < D) n.x = normals_row[2 * j];
+      if (2 * j + 1 < D) n.y = normals_row[2 * j + 1];
+    } else if (2 * j < D) {
+      n = philox_normal_pair(seed, it, (uint32_t)j);
+    }
+    p[k].x = (2 * j < D) ? mul_rn(1.0 / sqrt(var[k].x), n.x) : 0.0;
+    p[k].y = (2 * j + 1 < D) ? mul_rn(1.0 / sqrt(var[k].y), n.y) : 0.0;
+  }
+}
+
+}  // namespace lmc

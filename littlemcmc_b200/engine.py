@@ -101,21 +101,11 @@ class FusedTarget:
         return t
 
 
-def run_transitions(kind, chains, target, *, n_trans, iter0, n_tune, params, seeds=None, tapes=None,
-                    trace=None, stats=None, knobs=None, stream=None):
-    """Enqueue `n_trans` transitions of every chain (lmc_nuts_sample / lmc_hmc_sample).  Returns (trace, stats)
-    device tensors [C, n_trans, D] and [C, n_trans, NSTATS].  Asynchronous on the current CUDA stream."""
-    lib = L.load()
+def _fill_base(a, kind, chains, *, n_trans, iter0, n_tune, params, seeds, tapes, trace, stats, knobs, stream):
+    """Fill an lmc_sampler_args (everything but target / workspace).  Returns the tensors that must outlive the launch."""
     dev = chains.device
     Cn, D = chains.n_chains, chains.ndim
-    if trace is None:
-        trace = torch.empty(Cn, n_trans, D, dtype=torch.float64, device=dev)
-    if stats is None:
-        stats = torch.empty(Cn, n_trans, L.NSTATS, dtype=torch.float64, device=dev)
-    assert trace.is_contiguous() or trace.stride(2) == 1
-    a = L.SamplerArgs()
     a.abi_version, a.n_chains, a.ndim, a.ld = L.ABI_VERSION, Cn, D, chains.ld
-    a.target = target.c_struct(dev)
     a.q, a.var = chains.q.data_ptr(), chains.var.data_ptr()
     a.adapt_mass, a.adapt_step_size = int(params["adapt_mass"]), int(params["adapt_step_size"])
     a.mean_fg, a.rawvar_fg = chains.mean_fg.data_ptr(), chains.rawvar_fg.data_ptr()
@@ -144,24 +134,175 @@ def run_transitions(kind, chains, target, *, n_trans, iter0, n_tune, params, see
             raise ValueError("either per-chain seeds or tapes are required")
         a.rng.mode, a.rng.seeds = L.RNG_PHILOX, seeds.data_ptr()
         keep.append(seeds)
+    assert trace.stride(2) == 1
     a.trace, a.trace_chain_stride, a.trace_draw_stride = trace.data_ptr(), trace.stride(0), trace.stride(1)
     a.stats, a.status = stats.data_ptr(), chains.status.data_ptr()
     knobs = knobs or {}
     a.tune_group = int(knobs.get("group", 0))
     a.tune_smem_vecs = int(knobs.get("smem_vecs", -1))
     a.tune_max_slots = int(knobs.get("max_slots", 0))
+    a.stream = (stream or torch.cuda.current_stream(dev)).cuda_stream
+    return keep
+
+
+def _alloc_outputs(chains, n_trans, trace, stats):
+    dev, Cn, D = chains.device, chains.n_chains, chains.ndim
+    if trace is None:
+        trace = torch.empty(Cn, n_trans, D, dtype=torch.float64, device=dev)
+    if stats is None:
+        stats = torch.empty(Cn, n_trans, L.NSTATS, dtype=torch.float64, device=dev)
+    return trace, stats
+
+
+def run_transitions(kind, chains, target, *, n_trans, iter0, n_tune, params, seeds=None, tapes=None,
+                    trace=None, stats=None, knobs=None, stream=None):
+    """Enqueue `n_trans` transitions of every chain (lmc_nuts_sample / lmc_hmc_sample).  Returns (trace, stats)
+    device tensors [C, n_trans, D] and [C, n_trans, NSTATS].  Asynchronous on the current CUDA stream."""
+    lib = L.load()
+    dev = chains.device
+    Cn, D = chains.n_chains, chains.ndim
+    trace, stats = _alloc_outputs(chains, n_trans, trace, stats)
+    a = L.SamplerArgs()
     with torch.cuda.device(dev):
+        keep = _fill_base(a, kind, chains, n_trans=n_trans, iter0=iter0, n_tune=n_tune, params=params, seeds=seeds,
+                          tapes=tapes, trace=trace, stats=stats, knobs=knobs, stream=stream)
+        a.target = target.c_struct(dev)
         nbytes = lib.lmc_workspace_bytes(kind, Cn, D, a.max_treedepth, a.tune_group)
         if nbytes < 0:
             L.check(int(nbytes), "lmc_workspace_bytes")
         ws = chains.workspace(nbytes)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
-        a.stream = (stream or torch.cuda.current_stream(dev)).cuda_stream
         fn = lib.lmc_nuts_sample if kind == L.KIND_NUTS else lib.lmc_hmc_sample
         L.check(fn(C.byref(a)), "lmc_nuts_sample" if kind == L.KIND_NUTS else "lmc_hmc_sample")
     for t in keep:  # tensors referenced by the enqueued kernel must outlive it on this stream
         t.record_stream(torch.cuda.current_stream(dev)) if t.is_cuda else None
     return trace, stats
+
+
+# ---- callback mode -----------------------------------------------------------------------------------------------------
+def evaluate_callback(f, q):
+    """Evaluate a user callback for every chain.  `q`: device tensor [C, D] float64.  -> (logp [C], grad [C, D]) on
+    the device.  A `targets.TorchBatched` callable gets the whole batch (one torch op); any other callable is the
+    reference's per-chain NumPy contract `f(q[D]) -> (logp, dlogp[D])` (base_hmc.py:34) and is looped over on the host."""
+    from .targets import TorchBatched
+    Cn, D = q.shape
+    if isinstance(f, TorchBatched):
+        logp, grad = f(q)
+        if logp.shape != (Cn,) and logp.numel() == Cn:
+            logp = logp.reshape(Cn)
+        if logp.shape != (Cn,) or grad.shape != (Cn, D):
+            raise ValueError("batched callback must return (logp[%d], grad[%d, %d]); got %s, %s"
+                             % (Cn, Cn, D, tuple(logp.shape), tuple(grad.shape)))
+        return logp.to(torch.float64), grad.to(torch.float64)
+    qh = q.cpu().numpy()
+    logps, gh = np.empty(Cn), np.empty((Cn, D))
+    for c in range(Cn):
+        lp, gr = f(qh[c])
+        logps[c] = float(np.asarray(lp, dtype="d").reshape(-1)[0])   # 0-d or shape-(1,) logp (tests/test_utils.py:19-28)
+        gh[c] = np.asarray(gr, dtype="d").reshape(D)
+    return torch.as_tensor(logps, device=q.device), torch.as_tensor(gh, device=q.device)
+
+
+class CallbackRun:
+    """One callback-mode run: `n_trans` transitions of every chain driven by lmc_callback_begin / lmc_callback_advance
+    around a user gradient callback.  The loop body (callback + advance) can be captured in a CUDA graph."""
+
+    def __init__(self, kind, chains, callback, *, n_trans, iter0, n_tune, params, seeds=None, tapes=None, trace=None,
+                 stats=None, stream=None):
+        self.lib = L.load()
+        self.kind, self.chains, self.callback = kind, chains, callback
+        dev, Cn, D = chains.device, chains.n_chains, chains.ndim
+        self.trace, self.stats = _alloc_outputs(chains, n_trans, trace, stats)
+        self.q_eval = torch.zeros(Cn, chains.ld, dtype=torch.float64, device=dev)
+        self.g_eval = torch.zeros(Cn, chains.ld, dtype=torch.float64, device=dev)
+        self.logp_eval = torch.zeros(Cn, dtype=torch.float64, device=dev)
+        self.n_running = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.n_running_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.c = L.CallbackArgs()
+        with torch.cuda.device(dev):
+            self.keep = _fill_base(self.c.base, kind, chains, n_trans=n_trans, iter0=iter0, n_tune=n_tune, params=params,
+                                   seeds=seeds, tapes=tapes, trace=self.trace, stats=self.stats, knobs=None, stream=stream)
+            nbytes = self.lib.lmc_callback_state_bytes(kind, Cn, D, self.c.base.max_treedepth)
+            if nbytes < 0:
+                L.check(int(nbytes), "lmc_callback_state_bytes")
+            self.machine = chains.workspace(nbytes)
+        c = self.c
+        c.q_eval, c.g_eval, c.logp_eval = self.q_eval.data_ptr(), self.g_eval.data_ptr(), self.logp_eval.data_ptr()
+        c.machine, c.machine_bytes, c.n_running = self.machine.data_ptr(), self.machine.numel(), self.n_running.data_ptr()
+        per = (1 << c.base.max_treedepth) + 1 if kind == L.KIND_NUTS else c.base.max_steps + 1
+        self.max_iters = int(n_trans) * per + 1
+        self.n_evals = 0
+
+    def _stream_ptr(self):
+        return torch.cuda.current_stream(self.chains.device).cuda_stream
+
+    def begin(self):
+        self.c.base.stream = self._stream_ptr()
+        L.check(self.lib.lmc_callback_begin(self.kind, C.byref(self.c)), "lmc_callback_begin")
+
+    def iteration(self):
+        """callback at q_eval, then advance every chain (one gradient evaluation per chain)."""
+        D = self.chains.ndim
+        logp, grad = evaluate_callback(self.callback, self.q_eval[:, :D])
+        self.g_eval[:, :D].copy_(grad)
+        self.logp_eval.copy_(logp)
+        self.c.base.stream = self._stream_ptr()
+        L.check(self.lib.lmc_callback_advance(self.kind, C.byref(self.c)), "lmc_callback_advance")
+        self.n_evals += 1
+
+    def run(self, cuda_graph=False, iters_per_graph=8, poll=4):
+        dev = self.chains.device
+        with torch.cuda.device(dev):
+            self.begin()
+            if cuda_graph:
+                self._run_graphed(iters_per_graph)
+            else:
+                ev, it = None, 0
+                while it < self.max_iters:
+                    self.iteration()
+                    it += 1
+                    if it % poll == 0:
+                        # non-blocking poll: look at the counter copied `poll` iterations ago
+                        if ev is not None and ev.query() and int(self.n_running_host[0]) == 0:
+                            break
+                        if ev is None or ev.query():
+                            self.n_running_host.copy_(self.n_running, non_blocking=True)
+                            ev = torch.cuda.Event()
+                            ev.record()
+                if int(self.n_running.item()) != 0:
+                    raise L.LmcError("callback mode: chains still running after %d gradient evaluations" % it)
+        return self.trace, self.stats
+
+    def _run_graphed(self, iters_per_graph):
+        dev = self.chains.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):       # warm the callback up outside capture (lazy init, autotune, allocations)
+            evaluate_callback(self.callback, self.q_eval[:, :self.chains.ndim])
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        before = self.n_evals
+        with torch.cuda.graph(graph):
+            for _ in range(iters_per_graph):
+                self.iteration()
+        self.n_evals = before
+        it = 0
+        while it < self.max_iters:
+            graph.replay()
+            it += iters_per_graph
+            self.n_evals += iters_per_graph
+            if int(self.n_running.item()) == 0:   # one sync per replay (iters_per_graph gradient evaluations)
+                return
+        raise L.LmcError("callback mode: chains still running after %d gradient evaluations" % it)
+
+
+def run_transitions_callback(kind, chains, callback, *, n_trans, iter0, n_tune, params, seeds=None, tapes=None,
+                             trace=None, stats=None, cuda_graph=False):
+    """Callback-mode counterpart of run_transitions (synchronous: returns when every chain has finished)."""
+    run = CallbackRun(kind, chains, callback, n_trans=n_trans, iter0=iter0, n_tune=n_tune, params=params, seeds=seeds,
+                      tapes=tapes, trace=trace, stats=stats)
+    run.run(cuda_graph=cuda_graph)
+    return run.trace, run.stats
 
 
 def rng_fill(seeds, ndim, iter0, n_trans, u_stride):

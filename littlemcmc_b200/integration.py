@@ -17,8 +17,8 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from .engine import padded_ld
-from .targets import TorchBatched, fused_descriptor
+from .engine import evaluate_callback, padded_ld
+from .targets import fused_descriptor
 
 State = namedtuple("State", "q, p, v, q_grad, energy, model_logp")
 
@@ -73,23 +73,10 @@ class GpuLeapfrogIntegrator:
 
     def _callback(self, q_rows, D):
         """Evaluate a non-fused callback for every chain: -> (logp [C], grad [C, ld]) on the device."""
-        f = self._logp_dlogp_func
-        Cn = q_rows.shape[0]
+        logp, grad = evaluate_callback(self._logp_dlogp_func, q_rows[:, :D])
         g = torch.zeros_like(q_rows)
-        if isinstance(f, TorchBatched):
-            logp, grad = f(q_rows[:, :D])
-            g[:, :D] = grad
-            return logp.to(torch.float64).reshape(Cn).contiguous(), g
-        # reference-style NumPy callback, one chain at a time on the host
-        qh = q_rows[:, :D].cpu().numpy()
-        logps = np.empty(Cn)
-        gh = np.empty((Cn, D))
-        for c in range(Cn):
-            lp, gr = f(qh[c])
-            logps[c] = float(np.asarray(lp).reshape(-1)[0])
-            gh[c] = np.asarray(gr, dtype="d")
-        g[:, :D] = torch.as_tensor(gh, device=g.device)
-        return torch.as_tensor(logps, device=g.device), g
+        g[:, :D] = grad
+        return logp.contiguous(), g
 
     # -- the reference API -------------------------------------------------------------------------------------------
     def compute_state(self, q, p):

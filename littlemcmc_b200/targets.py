@@ -61,13 +61,31 @@ class NealFunnel:
 class TorchBatched:
     """Marks a batched device callback: ``fn(q: torch.Tensor[C, D] float64 cuda) -> (logp[C], grad[C, D])``.
 
-    It is evaluated on the current CUDA stream between the leapfrog half kernels (callback mode)."""
+    It is evaluated on the current CUDA stream between two launches of the sampler's state-machine kernel (callback
+    mode, csrc/lmc_callback.cu): one call per leapfrog step for ALL chains, instead of the reference's one call per
+    leapfrog step per chain (integration.py:115).  ``cuda_graph=True`` captures (callback + kernel) x 8 in a CUDA graph
+    and replays it; the callback must then be capture-safe (no host syncs, no data-dependent shapes)."""
 
-    def __init__(self, fn):
+    def __init__(self, fn, cuda_graph=False):
         self.fn = fn
+        self.cuda_graph = bool(cuda_graph)
 
     def __call__(self, q):
         return self.fn(q)
+
+    @classmethod
+    def from_logp(cls, logp_fn, cuda_graph=False):
+        """Build the callback from a scalar-per-chain log density ``logp_fn(q[C, D]) -> logp[C]`` with autograd
+        (chains are independent, so the gradient of ``logp.sum()`` is every chain's own gradient)."""
+        import torch
+
+        def fn(q):
+            with torch.enable_grad():
+                x = q.detach().requires_grad_(True)
+                lp = logp_fn(x)
+                (g,) = torch.autograd.grad(lp.sum(), x)
+            return lp.detach(), g
+        return cls(fn, cuda_graph=cuda_graph)
 
 
 def fused_descriptor(logp_dlogp_func):

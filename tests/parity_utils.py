@@ -127,6 +127,42 @@ def gpu_chains(case, n_chains, device="cuda:0"):
     return ch
 
 
+def torch_callback(case, device="cuda:0", cuda_graph=False):
+    """The case's target density as a batched torch op (targets.TorchBatched): the same formulas as the oracle's NumPy
+    callables (oracle/lmc_oracle.py diag_gaussian / neal_funnel), evaluated for all chains at once on the device."""
+    import torch
+    from littlemcmc_b200.targets import TorchBatched
+    D = int(case["ndim"])
+    if case["target"] == "diag_gaussian":
+        tau = torch.as_tensor(np.asarray(case["tau"], dtype="d"), device=device)
+
+        def fn(q):
+            g = -(tau * q)
+            return 0.5 * (q * g).sum(1), g
+        return TorchBatched(fn, cuda_graph=cuda_graph)
+    inv_s2, half_nm1 = 1.0 / 9.0, 0.5 * (D - 1)
+
+    def fn(q):
+        v, x = q[:, 0], q[:, 1:]
+        S = (x * x).sum(1)
+        ev = torch.exp(-v)
+        hs = 0.5 * ev * S
+        g = torch.empty_like(q)
+        g[:, 1:] = -(ev[:, None] * x)
+        g[:, 0] = -(v * inv_s2) + hs - half_nm1
+        return -(0.5 * v * v * inv_s2) - hs - half_nm1 * v, g
+    return TorchBatched(fn, cuda_graph=cuda_graph)
+
+
+def _launch(case, ch, tgt, callback, **kw):
+    """Fused kernel (callback None) or callback mode."""
+    from littlemcmc_b200 import engine
+    if callback is None:
+        return engine.run_transitions(_kind(case), ch, tgt, **kw)
+    kw.pop("knobs", None)
+    return engine.run_transitions_callback(_kind(case), ch, callback, **kw)
+
+
 def _kind(case):
     from littlemcmc_b200 import _lib as L
     return L.KIND_NUTS if str(case["kind"]) == "nuts" else L.KIND_HMC
@@ -139,7 +175,7 @@ def _read_state(ch):
     return ch.q[:, :D].cpu().numpy(), ch.var[:, :D].cpu().numpy(), wel.cpu().numpy(), ch.adapt[:, :9].cpu().numpy()
 
 
-def gpu_run_chained(case, tapes, chunks=1, knobs=None, device="cuda:0"):
+def gpu_run_chained(case, tapes, chunks=1, knobs=None, device="cuda:0", callback=None):
     """The whole run on the GPU, state carried on the device between `chunks` launches (run-level)."""
     import torch
     from littlemcmc_b200 import engine
@@ -152,16 +188,15 @@ def gpu_run_chained(case, tapes, chunks=1, knobs=None, device="cuda:0"):
     for lo, hi in zip(bounds[:-1], bounds[1:]):
         if hi == lo:
             continue
-        tr, st = engine.run_transitions(_kind(case), ch, tgt, n_trans=int(hi - lo), iter0=int(lo),
-                                        n_tune=int(case["tune"]), params=params,
-                                        tapes=(normals[:, lo:hi], uniforms[:, lo:hi]), knobs=knobs)
+        tr, st = _launch(case, ch, tgt, callback, n_trans=int(hi - lo), iter0=int(lo), n_tune=int(case["tune"]),
+                         params=params, tapes=(normals[:, lo:hi], uniforms[:, lo:hi]), knobs=knobs)
         traces.append(tr)
         stats.append(st)
     torch.cuda.synchronize()
     return torch.cat(traces, 1).cpu().numpy(), torch.cat(stats, 1).cpu().numpy(), ch
 
 
-def gpu_run_transitionwise(case, ora, knobs=None, device="cuda:0"):
+def gpu_run_transitionwise(case, ora, knobs=None, device="cuda:0", callback=None):
     """Transition-level protocol: before EVERY transition the device state of every chain is set to
     the oracle's state before that transition, so both sides see identical (q0, var, step-size state, Welford state,
     normals, uniform tape) and only one transition's arithmetic is compared -- differences cannot compound through
@@ -184,9 +219,8 @@ def gpu_run_transitionwise(case, ora, knobs=None, device="cuda:0"):
         for i, buf in enumerate((ch.mean_fg, ch.rawvar_fg, ch.mean_bg, ch.rawvar_bg)):
             buf[:, :D] = pre["welford"][:, t, i]
         ch.adapt[:, :9] = pre["adapt"][:, t]
-        _, st = engine.run_transitions(_kind(case), ch, tgt, n_trans=1, iter0=t, n_tune=int(case["tune"]),
-                                       params=params, tapes=(normals_d[:, t:t + 1], uniforms_d[:, t:t + 1]),
-                                       knobs=knobs)
+        _, st = _launch(case, ch, tgt, callback, n_trans=1, iter0=t, n_tune=int(case["tune"]), params=params,
+                        tapes=(normals_d[:, t:t + 1], uniforms_d[:, t:t + 1]), knobs=knobs)
         q, var, wel, ad = _read_state(ch)
         out_q.append(q); out_var.append(var); out_wel.append(wel); out_ad.append(ad)  # noqa: E702
         out_st.append(st[:, 0].cpu().numpy())
@@ -195,21 +229,28 @@ def gpu_run_transitionwise(case, ora, knobs=None, device="cuda:0"):
 
 
 def run_case_on_gpu_and_oracle(name, n_trans=None, knobs=None, device="cuda:0", chained=False,
-                               chunks=1) -> ParityResult:
+                               chunks=1, callback=None) -> ParityResult:
+    """`callback`: None = fused kernels; "torch" / "torch-graph" = callback mode with the case's density as a batched
+    torch op (eager / CUDA graph); "numpy" = callback mode with the oracle's per-chain NumPy callable."""
     from littlemcmc_b200 import _lib as L
     case, _ = gc.load(name)
     case = truncate_case(case, n_trans)
     ora = oracle_run(case)
     table = NUTS_STATS if str(case["kind"]) == "nuts" else HMC_STATS
+    if callback in ("torch", "torch-graph"):
+        callback = torch_callback(case, device, cuda_graph=(callback == "torch-graph"))
+    elif callback == "numpy":
+        callback = gc.target_fn(case)()
     if chained:
-        trace, st, ch = gpu_run_chained(case, ora["tapes"], chunks=chunks, knobs=knobs, device=device)
+        trace, st, ch = gpu_run_chained(case, ora["tapes"], chunks=chunks, knobs=knobs, device=device,
+                                        callback=callback)
         q, var, wel, ad = _read_state(ch)
         # only the final adaptation state is observable in a chained run
         return ParityResult(str(case["kind"]), trace, ora["trace"], {n: st[:, :, i] for n, i in table.items()},
                             ora["stats"], var[:, None], ora["post"]["var"][:, -1:], ad[:, None],
                             ora["post"]["adapt"][:, -1:], wel[:, None], ora["post"]["welford"][:, -1:],
                             st[:, :, L.STAT_N_UNIFORMS], ora["tapes"][2], ch.status.cpu().numpy())
-    q, var, wel, ad, st, ch = gpu_run_transitionwise(case, ora, knobs=knobs, device=device)
+    q, var, wel, ad, st, ch = gpu_run_transitionwise(case, ora, knobs=knobs, device=device, callback=callback)
     return ParityResult(str(case["kind"]), q, ora["trace"], {n: st[:, :, i] for n, i in table.items()}, ora["stats"],
                         var, ora["post"]["var"], ad, ora["post"]["adapt"], wel, ora["post"]["welford"],
                         st[:, :, L.STAT_N_UNIFORMS], ora["tapes"][2], ch.status.cpu().numpy())
