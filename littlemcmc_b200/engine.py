@@ -12,6 +12,10 @@ import torch
 from . import _lib as L
 
 
+# launches of this library's kernels enqueued by this process (bench.py reports the count inside its timed region)
+LAUNCH_COUNT = {"kernels": 0}
+
+
 def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -174,6 +178,7 @@ def run_transitions(kind, chains, target, *, n_trans, iter0, n_tune, params, see
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
         fn = lib.lmc_nuts_sample if kind == L.KIND_NUTS else lib.lmc_hmc_sample
         L.check(fn(C.byref(a)), "lmc_nuts_sample" if kind == L.KIND_NUTS else "lmc_hmc_sample")
+        LAUNCH_COUNT["kernels"] += 2      # sched_init_kernel + sampler_kernel
     for t in keep:  # tensors referenced by the enqueued kernel must outlive it on this stream
         t.record_stream(torch.cuda.current_stream(dev)) if t.is_cuda else None
     return trace, stats
@@ -239,6 +244,7 @@ class CallbackRun:
     def begin(self):
         self.c.base.stream = self._stream_ptr()
         L.check(self.lib.lmc_callback_begin(self.kind, C.byref(self.c)), "lmc_callback_begin")
+        LAUNCH_COUNT["kernels"] += 1
 
     def iteration(self):
         """callback at q_eval, then advance every chain (one gradient evaluation per chain)."""
@@ -249,6 +255,7 @@ class CallbackRun:
         self.c.base.stream = self._stream_ptr()
         L.check(self.lib.lmc_callback_advance(self.kind, C.byref(self.c)), "lmc_callback_advance")
         self.n_evals += 1
+        LAUNCH_COUNT["kernels"] += 1
 
     def run(self, cuda_graph=False, iters_per_graph=8, poll=4):
         dev = self.chains.device
@@ -291,6 +298,7 @@ class CallbackRun:
             graph.replay()
             it += iters_per_graph
             self.n_evals += iters_per_graph
+            LAUNCH_COUNT["kernels"] += iters_per_graph
             if int(self.n_running.item()) == 0:   # one sync per replay (iters_per_graph gradient evaluations)
                 return
         raise L.LmcError("callback mode: chains still running after %d gradient evaluations" % it)

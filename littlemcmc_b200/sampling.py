@@ -50,7 +50,7 @@ def sample(logp_dlogp_func, model_ndim, draws=1000, tune=1000, step=None, init="
     Differences a caller can observe: ``cores``, ``mp_ctx``, ``pickle_backend`` and ``progressbar`` are accepted and
     ignored (chains are a tensor dimension, there are no worker processes); ``start`` may also be ``[chains, ndim]``.
     Extra keywords: ``device`` (CUDA device, default current), ``block`` (transitions per launch, default: sized so a
-    trace block is <= 1 GiB), ``return_device`` (keep results as torch tensors on the GPU and skip the host copy).
+    trace block is <= 256 MiB, small enough that the copy-out of block i hides behind the sampling of block i+1), ``return_device`` (keep results as torch tensors on the GPU and skip the host copy).
     """
     if cores is None:
         cores = min(4, os.cpu_count() or 1)
@@ -83,7 +83,7 @@ def sample(logp_dlogp_func, model_ndim, draws=1000, tune=1000, step=None, init="
     keep_from = int(tune) if discard_tuned_samples else 0
     n_keep = T - keep_from
     if block is None:
-        block = max(1, min(T, (1 << 30) // max(1, chains * D * 8)))
+        block = max(1, min(T, (1 << 28) // max(1, chains * D * 8)))
     if return_device:
         trace_out = torch.empty(chains, n_keep, D, dtype=torch.float64, device=dev)
         host_trace = None

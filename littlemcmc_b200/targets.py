@@ -28,6 +28,16 @@ class DiagGaussian:
         g = -(self.tau * q)
         return 0.5 * np.dot(q, g), g
 
+    def torch_batched(self, device, cuda_graph=False):
+        """The same density as a batched torch op (callback mode instead of the fused kernel)."""
+        import torch
+        tau = torch.as_tensor(self.tau, dtype=torch.float64, device=device)
+
+        def fn(q):
+            g = -(tau * q)
+            return 0.5 * (q * g).sum(1), g
+        return TorchBatched(fn, cuda_graph=cuda_graph)
+
 
 class StdNormal(DiagGaussian):
     """Isotropic standard normal (BASELINE config 1)."""
@@ -56,6 +66,22 @@ class NealFunnel:
             g[0] = -(v * inv_s2) + hs - half_nm1
             logp = -(0.5 * v * v * inv_s2) - hs - half_nm1 * v
         return logp, g
+
+    def torch_batched(self, device=None, cuda_graph=False):
+        """The same density as a batched torch op (callback mode instead of the fused kernel)."""
+        import torch
+        inv_s2, half_nm1 = 1.0 / (self.v_scale * self.v_scale), 0.5 * (self.ndim - 1)
+
+        def fn(q):
+            v, x = q[:, 0], q[:, 1:]
+            S = (x * x).sum(1)
+            ev = torch.exp(-v)
+            hs = 0.5 * ev * S
+            g = torch.empty_like(q)
+            g[:, 1:] = -(ev[:, None] * x)
+            g[:, 0] = -(v * inv_s2) + hs - half_nm1
+            return -(0.5 * v * v * inv_s2) - hs - half_nm1 * v, g
+        return TorchBatched(fn, cuda_graph=cuda_graph)
 
 
 class TorchBatched:
