@@ -84,7 +84,7 @@ class BaseHMC:
                     target_accept=sa._target, gamma=sa._gamma, k=sa._k, t0=sa._t0, Emax=self.Emax)
 
     # ---- batched driver entry ----------------------------------------------------------------------------------------
-    def _run(self, n_trans, n_tune, tapes=None, trace=None, stats=None):
+    def _run(self, n_trans, n_tune, tapes=None, trace=None, stats=None, events=None):
         """`n_trans` transitions of every chain starting at `self.iter_count`; transitions with index < `n_tune` tune.
         Returns device tensors (trace [C, n_trans, D], stats [C, n_trans, NSTATS]).
 
@@ -96,11 +96,15 @@ class BaseHMC:
         common = dict(n_trans=n_trans, iter0=self.iter_count, n_tune=n_tune, params=self._params(), seeds=self._seeds,
                       tapes=tapes, trace=trace, stats=stats)
         if fused is not None:
-            tr, st = engine.run_transitions(self._kind, self._chains, fused, knobs=self._knobs, **common)
+            tr, st = engine.run_transitions(self._kind, self._chains, fused, knobs=self._knobs, events=events, **common)
         else:
             graph = bool(getattr(self._logp_dlogp_func, "cuda_graph", False))
+            if events is not None:
+                events[0].record()
             tr, st = engine.run_transitions_callback(self._kind, self._chains, self._logp_dlogp_func, cuda_graph=graph,
                                                      **common)
+            if events is not None:
+                events[1].record()
         self.iter_count += n_trans
         return tr, st
 

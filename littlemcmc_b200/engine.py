@@ -159,9 +159,11 @@ def _alloc_outputs(chains, n_trans, trace, stats):
 
 
 def run_transitions(kind, chains, target, *, n_trans, iter0, n_tune, params, seeds=None, tapes=None,
-                    trace=None, stats=None, knobs=None, stream=None):
+                    trace=None, stats=None, knobs=None, stream=None, events=None):
     """Enqueue `n_trans` transitions of every chain (lmc_nuts_sample / lmc_hmc_sample).  Returns (trace, stats)
-    device tensors [C, n_trans, D] and [C, n_trans, NSTATS].  Asynchronous on the current CUDA stream."""
+    device tensors [C, n_trans, D] and [C, n_trans, NSTATS].  Asynchronous on the current CUDA stream.
+    `events`: optional pair of torch.cuda.Event recorded on the launching stream immediately around the library call
+    (bench.py times the launch with them, so host-side argument marshalling is not inside the bracket)."""
     lib = L.load()
     dev = chains.device
     Cn, D = chains.n_chains, chains.ndim
@@ -177,7 +179,13 @@ def run_transitions(kind, chains, target, *, n_trans, iter0, n_tune, params, see
         ws = chains.workspace(nbytes)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
         fn = lib.lmc_nuts_sample if kind == L.KIND_NUTS else lib.lmc_hmc_sample
-        L.check(fn(C.byref(a)), "lmc_nuts_sample" if kind == L.KIND_NUTS else "lmc_hmc_sample")
+        launch_stream = stream or torch.cuda.current_stream(dev)
+        if events is not None:
+            events[0].record(launch_stream)
+        rc = fn(C.byref(a))
+        if events is not None:
+            events[1].record(launch_stream)
+        L.check(rc, "lmc_nuts_sample" if kind == L.KIND_NUTS else "lmc_hmc_sample")
         LAUNCH_COUNT["kernels"] += 2      # sched_init_kernel + sampler_kernel
     for t in keep:  # tensors referenced by the enqueued kernel must outlive it on this stream
         t.record_stream(torch.cuda.current_stream(dev)) if t.is_cuda else None
