@@ -110,9 +110,9 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
-        # 20 ms: dense enough for a ~50 ms timed region, sparse enough that NVML queries (which take driver locks)
+        # 10 ms: dense enough for a ~50 ms timed region, sparse enough that NVML queries (which take driver locks)
         # do not compete with the kernel launches of the loop being timed
-        self.period = 0.02
+        self.period = 0.01
         try:
             import pynvml
             pynvml.nvmlInit()

@@ -205,12 +205,12 @@ __global__ void __launch_bounds__(cb_block<G>()) cb_advance_kernel(const lmc_cal
         } else if (extend_top<G, NP>(sc, grp, tail, s.dir, var, q, p, cur_lp, cur_ps, cur, s.tr, next_uniform())) {
           trans_end = true;
         } else if (s.d + 1 < s.max_depth) {
-          const int base = tail + (s.dir > 0 ? T_RQ : T_LQ);  // self.right / self.left = tree.right (:304 / :313)
+          const int base = (s.dir > 0 ? T_RQ : T_LQ);  // self.right / self.left = tree.right (:304 / :313)
 #pragma unroll
           for (int k = 0; k < NP; ++k) {
-            sc.vec(base + 0)[k * G] = q[k];
-            sc.vec(base + 1)[k * G] = p[k];
-            sc.vec(base + 2)[k * G] = g[k];
+            sc.vec(tvid(tail, base + 0))[k * G] = q[k];
+            sc.vec(tvid(tail, base + 1))[k * G] = p[k];
+            sc.vec(tvid(tail, base + 2))[k * G] = g[k];
           }
           s.last_dir = s.dir;
           ++s.d;
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(cb_block<G>()) cb_advance_kernel(const lmc_cal
       stat_c = s.tr.max_dE;
       stat_logp = s.tr.prop_logp;
 #pragma unroll
-      for (int k = 0; k < NP; ++k) q[k] = sc.vec(tail + T_PROPQ)[k * G];  // hmc_step.end.q
+      for (int k = 0; k < NP; ++k) q[k] = sc.vec(tvid(tail, T_PROPQ))[k * G];  // hmc_step.end.q
     }
   }
 
@@ -317,12 +317,12 @@ __global__ void __launch_bounds__(cb_block<G>()) cb_advance_kernel(const lmc_cal
     if (new_doubling) {  // nuts.py:213 and the edge the new subtree grows from (:297 / :306)
       s.dir = (next_uniform() < 0.5) ? 1 : -1;
       if (s.last_dir != 0 && s.last_dir != s.dir) {
-        const int base = tail + (s.dir > 0 ? T_RQ : T_LQ);
+        const int base = (s.dir > 0 ? T_RQ : T_LQ);
 #pragma unroll
         for (int k = 0; k < NP; ++k) {
-          q[k] = sc.vec(base + 0)[k * G];
-          p[k] = sc.vec(base + 1)[k * G];
-          g[k] = sc.vec(base + 2)[k * G];
+          q[k] = sc.vec(tvid(tail, base + 0))[k * G];
+          p[k] = sc.vec(tvid(tail, base + 1))[k * G];
+          g[k] = sc.vec(tvid(tail, base + 2))[k * G];
         }
       }
       s.i = 0;

@@ -62,27 +62,49 @@ struct XF {
   double m;  // >= 0
   int e;
 };
-__device__ __forceinline__ XF xf_zero() { return XF{0.0, -(1 << 28)}; }
+// Fast path / wide path.  A leaf weight is exp(-dE) with |dE| < Emax (1000 by default): almost always |dE| is small, the
+// weight is an ordinary double and every XF in the tree has e == 0, so add / compare are one DADD / one DMUL + compare.
+// Only when |x| > kXfFast does a value carry a nonzero exponent; operations that meet one take the (out-of-line) wide
+// path.  Invariant: m == 0, or 2^-600 < m < 2^300 -- sums of <= 2^16 fast-path weights (each within 2^+-254) and
+// their squares stay normal doubles.
+constexpr double kXfFast = 176.0;  // exp(+-176) = 2^+-253.9
+__device__ __forceinline__ XF xf_zero() { return XF{0.0, 0}; }
 __device__ __forceinline__ XF xf_one() { return XF{1.0, 0}; }
+__device__ __forceinline__ double xf_scale(double m, int d) {  // m * 2^d, d <= 0, flushing to 0 far below
+  return d < -1000 ? 0.0 : m * __longlong_as_double((long long)(1023 + d) << 52);
+}
 // exp(x) for finite x of any magnitude: x = n ln2 + r, |r| <= ln2/2 (Cody-Waite, fdlibm's split of ln2)
-__device__ __forceinline__ XF xf_exp(double x) {
+static __device__ __noinline__ XF xf_exp_wide(double x) {
   const double n = rint(x * 1.44269504088896338700e+00);
   double r = fma(-n, 6.93147180369123816490e-01, x);
   r = fma(-n, 1.90821492927058770002e-10, r);
   return XF{exp(r), (int)n};
 }
-__device__ __forceinline__ double xf_scale(double m, int d) {  // m * 2^d, d <= 0, flushing to 0 far below
-  return d < -1000 ? 0.0 : m * __longlong_as_double((long long)(1023 + d) << 52);
+__device__ __forceinline__ XF xf_exp(double x) {
+  if (fabs(x) <= kXfFast) return XF{exp(x), 0};
+  return xf_exp_wide(x);
 }
-__device__ __forceinline__ XF xf_add(XF a, XF b) {
+static __device__ __noinline__ XF xf_add_wide(XF a, XF b) {
+  if (a.m == 0.0) return b;
+  if (b.m == 0.0) return a;
   const int e = a.e > b.e ? a.e : b.e;
   return XF{xf_scale(a.m, a.e - e) + xf_scale(b.m, b.e - e), e};
 }
+__device__ __forceinline__ XF xf_add(XF a, XF b) {
+  if (a.e == b.e) return XF{a.m + b.m, a.e};
+  return xf_add_wide(a, b);
+}
 __device__ __forceinline__ XF xf_sqr(XF a) { return XF{a.m * a.m, 2 * a.e}; }
 // u * a < b   (u in [0,1), a, b >= 0)
-__device__ __forceinline__ bool xf_u_less(double u, XF a, XF b) {
+static __device__ __noinline__ bool xf_u_less_wide(double u, XF a, XF b) {
+  if (b.m == 0.0) return false;
+  if (a.m == 0.0) return true;
   const int e = a.e > b.e ? a.e : b.e;
   return u * xf_scale(a.m, a.e - e) < xf_scale(b.m, b.e - e);
+}
+__device__ __forceinline__ bool xf_u_less(double u, XF a, XF b) {
+  if (a.e == b.e) return u * a.m < b.m;
+  return xf_u_less_wide(u, a, b);
 }
 __device__ __forceinline__ double xf_value(XF a) { return a.m == 0.0 ? 0.0 : scalbn(a.m, a.e); }
 __device__ __forceinline__ double xf_ratio(XF a, XF b) {  // a / b, b > 0
@@ -197,10 +219,10 @@ struct DiagGaussian {
     for (int k = 0; k < NP; ++k) {
       const int j = lane + k * G;
       const double2 t = (j < ldh) ? __ldg(tau + j) : make_double2(0.0, 0.0);
-      // g = -(tau * q): one rounding, the negation is exact.  Elements >= D have tau = q = 0.
+      // g = -(tau * q): one rounding, the negation is exact.
+      // Elements >= D: tau = 0 (zero-padded buffer / no load) and q = 0 (kept at exactly 0 in registers), so g = -0.0
+      // there, which leaves p and the sums unchanged -- no masking needed.
       g[k] = make_double2(-mul_rn(t.x, q[k].x), -mul_rn(t.y, q[k].y));
-      if (2 * j >= D) g[k].x = 0.0;
-      if (2 * j + 1 >= D) g[k].y = 0.0;
       part = dot2(part, q[k], g[k]);
     }
     return part;

@@ -224,12 +224,12 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
             // single double adjacent to 0.5)                                                          nuts.py:213
             const int dir = (next_uniform() < 0.5) ? 1 : -1;
             if (reg_edge != 0 && reg_edge != dir) {  // fetch the edge we extend from (nuts.py:297 / 306)
-              const int base = tail + (dir > 0 ? T_RQ : T_LQ);
+              const int base = (dir > 0 ? T_RQ : T_LQ);
 #pragma unroll
               for (int k = 0; k < NP; ++k) {
-                q[k] = sc.vec(base + 0)[k * G];
-                p[k] = sc.vec(base + 1)[k * G];
-                g[k] = sc.vec(base + 2)[k * G];
+                q[k] = sc.vec(tvid(tail, base + 0))[k * G];
+                p[k] = sc.vec(tvid(tail, base + 1))[k * G];
+                g[k] = sc.vec(tvid(tail, base + 2))[k * G];
               }
             }
             const double eps_d = dir > 0 ? eps : -eps;
@@ -244,13 +244,32 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
               double E, logp;
               leapfrog(tgt, grp, D, ldh, eps_d, q, p, g, var, E, logp);  // nuts.py:347
               ++n_leaves;
-              if (!leaf_init<NP>(E, logp, E0, a.Emax, p, tr.max_dE, cur, cur_lp, cur_ps)) {
+              if (!leaf_scalars(E, logp, E0, a.Emax, tr.max_dE, cur)) {
                 fail = 1;
                 break;
               }
-              unsigned jbits = i;
-              int lvl = 0;
-              while (jbits & 1u) {  // merge with the stack entry of this level (nuts.py:387-417)
+              if ((i & 1u) == 0u) {
+                // even leaf: it becomes stack entry 0 (the next leaf merges with it); the only even LAST leaf is the
+                // single leaf of the first doubling, which stays in registers as the whole subtree
+                if (i + 1 < n_leaf_total) {
+                  push_leaf<G, NP>(sc, ss, q, p, cur, free_slots);
+                  if constexpr (G == 32) __syncwarp();
+                } else {
+#pragma unroll
+                  for (int k = 0; k < NP; ++k) cur_lp[k] = cur_ps[k] = p[k];
+                }
+                continue;
+              }
+              // odd leaf: merge with stack entry 0, then with level 1, 2, .. for every further trailing 1-bit of i
+              // (nuts.py:387-417, post-order of the reference's recursion)
+              if (merge_leaf_pair<G, NP>(sc, grp, ss, var, p, cur_lp, cur_ps, cur, free_slots, next_uniform())) {
+                fail = 2;
+                break;
+              }
+              unsigned jbits = i >> 1;
+              int lvl = 1;
+              while (jbits & 1u) {
+                __builtin_assume(lvl >= 1);  // the level-0 branches of merge_level are dead here
                 if (merge_level<G, NP>(sc, grp, ss, lvl, var, p, cur_lp, cur_ps, cur, free_slots, next_uniform())) {
                   fail = 2;
                   break;
@@ -259,6 +278,7 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
                 ++lvl;
               }
               if (fail) break;
+              __builtin_assume(lvl >= 1);
               if (i + 1 < n_leaf_total) {  // push "cur" at level lvl (the last leaf's result stays in registers)
                 // One writer.  Readers see it after at least one group barrier (the next leaf's energy reduction)
                 // and finished reading the previous occupant before the barrier that preceded this point.
@@ -274,12 +294,12 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
             }
             if (extend_top<G, NP>(sc, grp, tail, dir, var, q, p, cur_lp, cur_ps, cur, tr, next_uniform())) break;  // :340
             if (d + 1 < max_depth) {  // self.right / self.left = tree.right (:304 / :313)
-              const int base = tail + (dir > 0 ? T_RQ : T_LQ);
+              const int base = (dir > 0 ? T_RQ : T_LQ);
 #pragma unroll
               for (int k = 0; k < NP; ++k) {
-                sc.vec(base + 0)[k * G] = q[k];
-                sc.vec(base + 1)[k * G] = p[k];
-                sc.vec(base + 2)[k * G] = g[k];
+                sc.vec(tvid(tail, base + 0))[k * G] = q[k];
+                sc.vec(tvid(tail, base + 1))[k * G] = p[k];
+                sc.vec(tvid(tail, base + 2))[k * G] = g[k];
               }
               reg_edge = dir;
             }
@@ -293,7 +313,7 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
           stat_c = tr.max_dE;
           stat_logp = tr.prop_logp;
 #pragma unroll
-          for (int k = 0; k < NP; ++k) q[k] = sc.vec(tail + T_PROPQ)[k * G];  // hmc_step.end.q
+          for (int k = 0; k < NP; ++k) q[k] = sc.vec(tvid(tail, T_PROPQ))[k * G];  // hmc_step.end.q
         } else {
           // ---- HamiltonianMC._hamiltonian_step (hmc.py:140-182) -------------------------------------------------
           double2 q0[NP];

@@ -17,15 +17,25 @@ namespace lmc {
 constexpr int kLeafProp = -1;  // "the proposal is the current leaf, still in registers"
 
 // scratch-vector ids (ordered hottest first; ids < n_smem_vecs are shared-memory resident in the fused kernel)
-//   0                 stack level 0: p  (left.p == right.p == p_sum for a single leaf)
-//   1, 2              proposal slots 0, 1
-//   3+4(l-1)+{0,1,2}  stack level l >= 1: left.p, right.p, p_sum
-//   3+4(l-1)+3        proposal slot l+1
-//   tail              trajectory edges L(q,p,g), R(q,p,g), trajectory p_sum, trajectory proposal q
-__host__ __device__ constexpr int vid_stack(int level, int which) { return level == 0 ? 0 : 3 + 4 * (level - 1) + which; }
-__host__ __device__ constexpr int vid_prop(int slot) { return slot < 2 ? 1 + slot : 4 * slot - 2; }
-__host__ __device__ constexpr int vid_tail(int max_depth) { return max_depth < 1 ? 3 : 4 * max_depth - 1; }
+//   0, 1, 2               trajectory p_sum, left edge p, right edge p  (read by every doubling's U-turn checks)
+//   3 + 0                 stack level 0: p  (left.p == right.p == p_sum for a single leaf)
+//   3 + {1, 2}            proposal slots 0, 1
+//   3 + 3+4(l-1)+{0,1,2}  stack level l >= 1: left.p, right.p, p_sum
+//   3 + 3+4(l-1)+3        proposal slot l+1
+//   tail + T_*            the rest of the trajectory state: edges' q and grad, trajectory proposal q
+// ids 0..2: the three trajectory vectors every doubling reads (p_sum, left.p, right.p) -- measured +5% at 1024 x 1000
+// over keeping them in the L2-resident tail
+constexpr int kHotTail = 3;
+__host__ __device__ constexpr int vid_stack(int level, int which) {
+  return kHotTail + (level == 0 ? 0 : 3 + 4 * (level - 1) + which);
+}
+__host__ __device__ constexpr int vid_prop(int slot) { return kHotTail + (slot < 2 ? 1 + slot : 4 * slot - 2); }
+__host__ __device__ constexpr int vid_tail(int max_depth) { return kHotTail + (max_depth < 1 ? 3 : 4 * max_depth - 1); }
 enum { T_LQ = 0, T_LP, T_LG, T_RQ, T_RP, T_RG, T_PSUM, T_PROPQ, T_COUNT };
+// id of trajectory vector `t` (T_*), `tail` = vid_tail(max_treedepth)
+__host__ __device__ constexpr int tvid(int tail, int t) {
+  return t == T_PSUM ? 0 : t == T_LP ? 1 : t == T_RP ? 2 : tail + t;
+}
 __host__ __device__ constexpr int ws_vecs_nuts(int max_depth) { return vid_tail(max_depth) + T_COUNT; }
 
 // per-level scalars of the subtree stack (written by lane 0 only; every read is separated from the write by a group
@@ -72,14 +82,14 @@ __device__ __forceinline__ void tree_init(const Scratch<G, NP>& sc, int tail, co
                                           const double2 (&p)[NP], const double2 (&g)[NP]) {
 #pragma unroll
   for (int k = 0; k < NP; ++k) {
-    sc.vec(tail + T_LQ)[k * G] = q[k];
-    sc.vec(tail + T_LP)[k * G] = p[k];
-    sc.vec(tail + T_LG)[k * G] = g[k];
-    sc.vec(tail + T_RQ)[k * G] = q[k];
-    sc.vec(tail + T_RP)[k * G] = p[k];
-    sc.vec(tail + T_RG)[k * G] = g[k];
-    sc.vec(tail + T_PSUM)[k * G] = p[k];
-    sc.vec(tail + T_PROPQ)[k * G] = q[k];
+    sc.vec(tvid(tail, T_LQ))[k * G] = q[k];
+    sc.vec(tvid(tail, T_LP))[k * G] = p[k];
+    sc.vec(tvid(tail, T_LG))[k * G] = g[k];
+    sc.vec(tvid(tail, T_RQ))[k * G] = q[k];
+    sc.vec(tvid(tail, T_RP))[k * G] = p[k];
+    sc.vec(tvid(tail, T_RG))[k * G] = g[k];
+    sc.vec(tvid(tail, T_PSUM))[k * G] = p[k];
+    sc.vec(tvid(tail, T_PROPQ))[k * G] = q[k];
   }
 }
 
@@ -170,6 +180,79 @@ __device__ __forceinline__ bool merge_level(const Scratch<G, NP>& sc, Group<G>& 
   return turn;
 }
 
+// ---- level-0 specialisations used by the fused kernel ------------------------------------------------------------------
+// A single leaf has left.p == right.p == p_sum == p, so it needs no cur_lp / cur_ps registers: an even leaf goes straight
+// to stack level 0 (push_leaf), an odd leaf is merged with it (merge_leaf_pair), which is where cur_lp / cur_ps are first
+// defined.  Same arithmetic, same order of operations and of uniforms as leaf_init + merge_level(lvl = 0) + push_cur.
+
+// scalar part of _single_step after the leapfrog (nuts.py:352-368).  Returns false when the leaf diverges.
+__device__ __forceinline__ bool leaf_scalars(double E, double logp, double E0, double Emax, double& max_dE, CurTree& cur) {
+  double dE = E - E0;                         // :352
+  if (isnan(dE)) dE = CUDART_INF;             // :353-354
+  if (fabs(dE) > fabs(max_dE)) max_dE = dE;   // :356-357
+  if (!(fabs(dE) < Emax)) return false;       // :358 / :370-375
+  cur.w = xf_exp(-dE);                                 // log_size = -dE
+  cur.a = (-dE < 0.0) ? xf_sqr(cur.w) : cur.w;         // log_p_accept_weighted = -dE + min(0, -dE)  (:363)
+  cur.pE = E;
+  cur.plogp = logp;
+  cur.pslot = kLeafProp;
+  return true;
+}
+
+// push the current leaf (state q, p) as stack entry 0
+template <int G, int NP>
+__device__ __forceinline__ void push_leaf(const Scratch<G, NP>& sc, StackScalars* ss, const double2 (&q)[NP],
+                                          const double2 (&p)[NP], CurTree& cur, unsigned& free_slots) {
+  cur.pslot = __ffs(free_slots) - 1;
+  free_slots &= ~(1u << cur.pslot);
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    sc.vec(vid_prop(cur.pslot))[k * G] = q[k];
+    sc.vec(vid_stack(0, 0))[k * G] = p[k];
+  }
+  if (sc.lane == 0) {
+    ss->wm[0] = cur.w.m;
+    ss->we[0] = cur.w.e;
+    ss->am[0] = cur.a.m;
+    ss->ae[0] = cur.a.e;
+    ss->pE[0] = cur.pE;
+    ss->plogp[0] = cur.plogp;
+    ss->pslot[0] = cur.pslot;
+  }
+}
+
+// merge stack entry 0 (a leaf) with the current leaf (momentum p): defines cur_lp, cur_ps.  Returns `turning`.
+template <int G, int NP>
+__device__ __forceinline__ bool merge_leaf_pair(const Scratch<G, NP>& sc, Group<G>& grp, const StackScalars* ss,
+                                                const double2 (&var)[NP], const double2 (&p)[NP], double2 (&cur_lp)[NP],
+                                                double2 (&cur_ps)[NP], CurTree& cur, unsigned& free_slots, double u) {
+  double d2[2] = {0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    const double2 t1p = sc.vec(vid_stack(0, 0))[k * G];
+    const double2 ps = add2(t1p, p[k]);            // p_sum = tree1.p_sum + tree2.p_sum (:390)
+    d2[0] = dot2(d2[0], ps, mul2(var[k], t1p));    // p_sum . left.v
+    d2[1] = dot2(d2[1], ps, mul2(var[k], p[k]));   // p_sum . right.v
+    cur_ps[k] = ps;
+    cur_lp[k] = t1p;
+  }
+  grp.allreduce(d2);
+  const bool turn = (d2[0] <= 0) || (d2[1] <= 0);  // :391
+  const XF nw = xf_add(XF{ss->wm[0], ss->we[0]}, cur.w);  // :400
+  const XF na = xf_add(XF{ss->am[0], ss->ae[0]}, cur.a);  // :401-403
+  const int t1_pslot = ss->pslot[0];
+  if (xf_u_less(u, nw, cur.w)) {  // keep tree2's proposal (the current leaf, still in registers)       (:404-407)
+    free_slots |= 1u << t1_pslot;
+  } else {
+    cur.pslot = t1_pslot;
+    cur.pE = ss->pE[0];
+    cur.plogp = ss->plogp[0];
+  }
+  cur.w = nw;
+  cur.a = na;
+  return turn;
+}
+
 // Push "cur" (right edge state q, p) as stack entry `lvl`.  One writer for the scalars (lane 0).
 template <int G, int NP>
 __device__ __forceinline__ void push_cur(const Scratch<G, NP>& sc, StackScalars* ss, int lvl, const double2 (&q)[NP],
@@ -215,10 +298,10 @@ __device__ __forceinline__ bool extend_top(const Scratch<G, NP>& sc, Group<G>& g
     tr.prop_logp = cur.plogp;
     if (cur.pslot == kLeafProp) {
 #pragma unroll
-      for (int k = 0; k < NP; ++k) sc.vec(tail + T_PROPQ)[k * G] = q[k];
+      for (int k = 0; k < NP; ++k) sc.vec(tvid(tail, T_PROPQ))[k * G] = q[k];
     } else {
 #pragma unroll
-      for (int k = 0; k < NP; ++k) sc.vec(tail + T_PROPQ)[k * G] = sc.vec(vid_prop(cur.pslot))[k * G];
+      for (int k = 0; k < NP; ++k) sc.vec(tvid(tail, T_PROPQ))[k * G] = sc.vec(vid_prop(cur.pslot))[k * G];
     }
   }
   tr.Wp = xf_add(tr.Wp, cur.w);    // log_size = logaddexp(log_size, tree.log_size)                     (:325)
@@ -226,9 +309,9 @@ __device__ __forceinline__ bool extend_top(const Scratch<G, NP>& sc, Group<G>& g
   double d6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
   for (int k = 0; k < NP; ++k) {
-    const double2 psum = add2(sc.vec(tail + T_PSUM)[k * G], cur_ps[k]);  // self.p_sum[:] += tree.p_sum (:329)
-    sc.vec(tail + T_PSUM)[k * G] = psum;
-    const double2 oLp = sc.vec(tail + T_LP)[k * G], oRp = sc.vec(tail + T_RP)[k * G];  // old edges' momenta
+    const double2 psum = add2(sc.vec(tvid(tail, T_PSUM))[k * G], cur_ps[k]);  // self.p_sum[:] += tree.p_sum (:329)
+    sc.vec(tvid(tail, T_PSUM))[k * G] = psum;
+    const double2 oLp = sc.vec(tvid(tail, T_LP))[k * G], oRp = sc.vec(tvid(tail, T_RP))[k * G];  // old edges' momenta
     const double2 voL = mul2(var[k], oLp), voR = mul2(var[k], oRp);
     const double2 vTl = mul2(var[k], cur_lp[k]), vTr = mul2(var[k], p[k]);
     if (dir > 0) {

@@ -12,16 +12,19 @@ def mk():
     pot = lmc.QuadPotentialDiagAdapt(D, np.zeros(D), np.ones(D), 10)
     return lmc.NUTS(target, D, potential=pot, max_treedepth=10)
 step = mk()
-def call(block, ret_dev, seed):
+TM = {}
+def call(block, ret_dev, seed, hw="copy"):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     tr, st = lmc.sample(target, D, draws=T // 2, tune=T // 2, step=step, chains=C_, start=start.numpy(),
                         random_seed=list(1000 + seed + np.arange(C_)), discard_tuned_samples=False, device=dev,
-                        progressbar=False, block=block, return_device=ret_dev)
+                        progressbar=False, block=block, return_device=ret_dev, host_write=hw, _timing=TM)
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
     n = float(st["tree_size"].sum())
     return dt, n
 call(None, False, 0); call(None, True, 0)
-for block in (None, 4, 8, 16, 32, 64):
-    for ret_dev in (True, False):
-        dt, n = min(call(block, ret_dev, s) for s in (1, 2, 3))
-        print("block=%s return_device=%s: %.1f ms, %.3e leapfrog/s (%d leapfrogs)" % (block, ret_dev, dt * 1e3, n / dt, n), flush=True)
+for block in (None,):
+    for mode in ("device", "copy", "direct"):
+        dt, n = min(call(block, mode == "device", s, mode if mode != "device" else "copy") for s in (1, 2, 3))
+        TM.clear(); call(block, mode == "device", 9, mode if mode != "device" else "copy")
+        print("   ", {k: round(v, 1) for k, v in TM.items()})
+        print("block=%s %s: %.1f ms, %.3e leapfrog/s (%d leapfrogs)" % (block, mode, dt * 1e3, n / dt, n), flush=True)
