@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define LMC_ABI_VERSION 1
+#define LMC_ABI_VERSION 2
 
 #define LMC_OK 0
 #define LMC_ERR_BADARG (-1)      /* null pointer, bad size/stride/alignment */
@@ -74,7 +74,7 @@ typedef struct lmc_rng {
 #define LMC_ADAPT_STRIDE 10
 
 /* ---- per-transition statistics: stats[(chain * n_trans + t) * LMC_NSTATS + k], all float64 ------------ */
-#define LMC_NSTATS 12
+#define LMC_NSTATS 13
 /* NUTS (nuts.py:87-101, 427-435)                 HMC (hmc.py:36-50, 173-181)                              */
 #define LMC_STAT_DEPTH 0           /* depth            | n_steps                                           */
 #define LMC_STAT_TREE_SIZE 1       /* tree_size        | path_length                                       */
@@ -88,6 +88,8 @@ typedef struct lmc_rng {
 #define LMC_STAT_STEP_SIZE 9       /* step_size  (post-update: the NEXT draw's, base_hmc.py:161,188)       */
 #define LMC_STAT_STEP_SIZE_BAR 10  /* step_size_bar                                                        */
 #define LMC_STAT_N_UNIFORMS 11     /* uniforms consumed by this transition (bookkeeping, not in reference) */
+#define LMC_STAT_REACHED_MAX_TREEDEPTH 12 /* NUTS: 1 when the doubling loop ran out without a divergence or a U-turn
+                                      (the `else` of nuts.py:212-220, what NUTS._reached_max_treedepth counts); HMC: 0 */
 
 /* ---- status bits: status[chain] ------------------------------------------------------------------------ */
 #define LMC_STATUS_BAD_INITIAL_ENERGY 1 /* non-finite start energy: the reference raises ValueError
@@ -144,6 +146,12 @@ typedef struct lmc_sampler_args {
   int64_t trace_draw_stride;
   double* stats;       /* [n_chains, n_trans, LMC_NSTATS]                                                   */
   int32_t* status;     /* [n_chains] OR-ed LMC_STATUS_* bits                                                */
+
+  /* BaseHMC.step_rand (base_hmc.py:154-155): the reference passes the current step size through a user hook before
+   * every transition.  NULL: no hook.  Otherwise [n_chains] step sizes that REPLACE step_adapt.current() for every
+   * transition of this call (the host layer evaluates the hook and launches one transition at a time); the
+   * dual-averaging update still runs on its own state, as in the reference. */
+  const double* step_size_override;
 
   /* scratch and launch control */
   void* workspace;     /* >= lmc_workspace_bytes(...) bytes, 16-byte aligned                                */

@@ -6,16 +6,17 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("LMC_LIB_PATH") or os.path.join(_HERE, "liblmc_b200.so")  # env: kernel experiments only
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 OK, ERR_BADARG, ERR_UNSUPPORTED, ERR_LAUNCH, ERR_WORKSPACE = 0, -1, -2, -3, -4
 TARGET_DIAG_GAUSSIAN, TARGET_FUNNEL = 0, 1
 RNG_TAPE, RNG_PHILOX = 0, 1
 KIND_NUTS, KIND_HMC = 0, 1
 ADAPT_LOG_STEP, ADAPT_LOG_BAR, ADAPT_HBAR, ADAPT_COUNT, ADAPT_MU = 0, 1, 2, 3, 4
 ADAPT_W_FG, ADAPT_W_BG, ADAPT_NSAMPLES, ADAPT_WINDOW, ADAPT_STRIDE = 5, 6, 7, 8, 10
-NSTATS = 12
+NSTATS = 13
 (STAT_DEPTH, STAT_TREE_SIZE, STAT_ACCEPT, STAT_ENERGY, STAT_ENERGY_ERROR, STAT_MAX_ENERGY_ERROR, STAT_MODEL_LOGP,
- STAT_DIVERGING, STAT_TUNE, STAT_STEP_SIZE, STAT_STEP_SIZE_BAR, STAT_N_UNIFORMS) = range(12)
+ STAT_DIVERGING, STAT_TUNE, STAT_STEP_SIZE, STAT_STEP_SIZE_BAR, STAT_N_UNIFORMS,
+ STAT_REACHED_MAX_TREEDEPTH) = range(13)
 STATUS_BAD_INITIAL_ENERGY, STATUS_TAPE_EXHAUSTED = 1, 2
 
 _ERR_NAMES = {ERR_BADARG: "LMC_ERR_BADARG", ERR_UNSUPPORTED: "LMC_ERR_UNSUPPORTED", ERR_LAUNCH: "LMC_ERR_LAUNCH",
@@ -45,7 +46,7 @@ class SamplerArgs(C.Structure):
         ("path_length", C.c_double), ("max_steps", C.c_int32), ("reserved2", C.c_int32),
         ("rng", Rng),
         ("trace", C.c_void_p), ("trace_chain_stride", C.c_int64), ("trace_draw_stride", C.c_int64),
-        ("stats", C.c_void_p), ("status", C.c_void_p),
+        ("stats", C.c_void_p), ("status", C.c_void_p), ("step_size_override", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("stream", C.c_void_p),
         ("tune_group", C.c_int32), ("tune_smem_vecs", C.c_int32), ("tune_max_slots", C.c_int32),
         ("reserved3", C.c_int32),

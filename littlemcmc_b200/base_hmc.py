@@ -41,10 +41,13 @@ class BaseHMC:
             raise ValueError("Cannot specify both `potential` and `scaling`.")
         self.potential = potential if potential is not None else quad_potential(np.asarray(scaling), is_cov)
         self.integrator = integration.GpuLeapfrogIntegrator(self.potential, self._logp_dlogp_func)
-        if step_rand is not None:
-            raise NotImplementedError("step_rand (a per-transition Python hook) is not part of the GPU hot path "
-                                      "(SURVEY.md section 8f, rank 4)")
-        self._step_rand = None
+        # base_hmc.py:154-155: `step_size = self.step_rand(step_size)` before every transition.  Here the hook gets the
+        # step sizes of ALL chains as one float64 array [n_chains] (a function written for a scalar that uses NumPy
+        # arithmetic works unchanged; one that does not is called once per chain).  A hook forces one launch per
+        # transition, because it is host code that must run between transitions.
+        if step_rand is not None and not callable(step_rand):
+            raise TypeError("step_rand must be callable")
+        self._step_rand = step_rand
         self._warnings = []
         self._samples_after_tune = 0
         self._num_divs_sample = 0
@@ -93,8 +96,13 @@ class BaseHMC:
         NumPy callable -- runs in callback mode: the callback is evaluated for all chains between two launches
         (engine.CallbackRun); that path returns when every chain has finished."""
         fused = self._fused_target()
+        if self._step_rand is not None and n_trans > 1:
+            return self._run_with_step_rand(n_trans, n_tune, tapes, trace, stats)
+        override = None
+        if self._step_rand is not None:
+            override = self._apply_step_rand(self.iter_count < n_tune)
         common = dict(n_trans=n_trans, iter0=self.iter_count, n_tune=n_tune, params=self._params(), seeds=self._seeds,
-                      tapes=tapes, trace=trace, stats=stats)
+                      tapes=tapes, trace=trace, stats=stats, step_size_override=override)
         if fused is not None:
             tr, st = engine.run_transitions(self._kind, self._chains, fused, knobs=self._knobs, events=events, **common)
         else:
@@ -107,6 +115,32 @@ class BaseHMC:
                 events[1].record()
         self.iter_count += n_trans
         return tr, st
+
+    def _apply_step_rand(self, tuning):
+        """Current step size of every chain (step_sizes.py:58-69) passed through the user's hook (base_hmc.py:154-155)."""
+        eps = self.step_adapt.current_all(tuning and bool(self.adapt_step_size)).cpu().numpy()
+        out = None
+        try:
+            out = np.asarray(self._step_rand(eps), dtype="d")
+        except Exception:           # a hook written for Python scalars only
+            out = None
+        if out is None or out.shape != eps.shape:
+            out = np.array([float(self._step_rand(float(e))) for e in eps], dtype="d")
+        return torch.as_tensor(out, device=self._chains.device)
+
+    def _run_with_step_rand(self, n_trans, n_tune, tapes, trace, stats):
+        """One launch per transition, the hook evaluated on the host in between."""
+        Cn, D, dev = self._chains.n_chains, self.model_ndim, self._chains.device
+        if trace is None:
+            trace = torch.empty(Cn, n_trans, D, dtype=torch.float64, device=dev)
+        if stats is None:
+            stats = torch.empty(Cn, n_trans, L.NSTATS, dtype=torch.float64, device=dev)
+        for t in range(n_trans):
+            tp = None if tapes is None else (tapes[0][:, t:t + 1], tapes[1][:, t:t + 1])
+            st1 = torch.empty(Cn, 1, L.NSTATS, dtype=torch.float64, device=dev)
+            self._run(1, n_tune, tapes=tp, trace=trace[:, t:t + 1], stats=st1)
+            stats[:, t:t + 1] = st1
+        return trace, stats
 
     def _check_status(self):
         status = self._chains.status

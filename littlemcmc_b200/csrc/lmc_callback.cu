@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(cb_block<G>()) cb_advance_kernel(const lmc_cal
     return u;
   };
 
-  bool new_doubling = false, trans_end = false, dead = false, diverging = false;
+  bool new_doubling = false, trans_end = false, dead = false, diverging = false, reached_max = false;
   double accept_stat = 0.0, stat_a = 0.0, stat_b = 0.0, stat_energy = 0.0, stat_energy_error = 0.0, stat_c = 0.0,
          stat_logp = 0.0;
 
@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(cb_block<G>()) cb_advance_kernel(const lmc_cal
       dead = true;
     } else {
       s.eps = exp(adapt_step ? ad[LMC_ADAPT_LOG_STEP] : ad[LMC_ADAPT_LOG_BAR]);  // step_sizes.py:58-69
+      if (a.step_size_override) s.eps = a.step_size_override[chain];             // step_rand hook, base_hmc.py:154-155
       if constexpr (KIND == KIND_NUTS) {
         s.max_depth = (tune && it < 200) ? a.early_max_treedepth : a.max_treedepth;  // nuts.py:205-208
         s.tr = TrajScalars{xf_zero(), xf_zero(), 0.0, s.E0, logp, 0, 0};
@@ -154,6 +155,7 @@ __global__ void __launch_bounds__(cb_block<G>()) cb_advance_kernel(const lmc_cal
         tree_init<G, NP>(sc, tail, q, p, g);
         new_doubling = s.max_depth > 0;
         trans_end = !new_doubling;
+        reached_max = trans_end;  // for/else of nuts.py:212-220 with an empty range
       } else {
         s.path_length = next_uniform() * a.path_length;             // hmc.py:141
         s.n_steps = hmc_n_steps(s.path_length, s.eps, a.max_steps);  // :142-143
@@ -217,6 +219,7 @@ __global__ void __launch_bounds__(cb_block<G>()) cb_advance_kernel(const lmc_cal
           new_doubling = true;
         } else {
           trans_end = true;  // max_treedepth reached (nuts.py:218-220)
+          reached_max = true;
         }
       }
     } else {
@@ -290,6 +293,7 @@ __global__ void __launch_bounds__(cb_block<G>()) cb_advance_kernel(const lmc_cal
       srow[LMC_STAT_STEP_SIZE] = exp(da.log_step);
       srow[LMC_STAT_STEP_SIZE_BAR] = exp(da.log_bar);
       srow[LMC_STAT_N_UNIFORMS] = (double)s.uc;
+      srow[LMC_STAT_REACHED_MAX_TREEDEPTH] = reached_max ? 1.0 : 0.0;
       ad[LMC_ADAPT_LOG_STEP] = da.log_step;
       ad[LMC_ADAPT_LOG_BAR] = da.log_bar;
       ad[LMC_ADAPT_HBAR] = da.hbar;

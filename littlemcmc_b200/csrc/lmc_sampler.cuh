@@ -208,10 +208,11 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
         status |= LMC_STATUS_BAD_INITIAL_ENERGY;
         dead = true;
       } else {
-        const double eps = exp(adapt_step ? da.log_step : da.log_bar);  // step_sizes.py:58-69
+        double eps = exp(adapt_step ? da.log_step : da.log_bar);  // step_sizes.py:58-69
+        if (a.step_size_override) eps = __ldg(a.step_size_override + chain);  // step_rand hook, base_hmc.py:154-155
 
         double accept_stat, stat_a, stat_b, stat_energy, stat_energy_error, stat_c, stat_logp;
-        bool diverging = false;
+        bool diverging = false, reached_max = false;
 
         if constexpr (KIND == KIND_NUTS) {
           // ---- NUTS._hamiltonian_step + _Tree  (nuts.py:204-224, 251-435) ---------------------------------------
@@ -219,6 +220,7 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
           TrajScalars tr{xf_zero(), xf_zero(), 0.0, E0, logp0, 0, 0};
           int reg_edge = 0;  // which trajectory edge (q,p,g) currently sits in registers: 0 both (start), +1 R, -1 L
           tree_init<G, NP>(sc, tail, q, p, g);
+          reached_max = max_depth <= 0;          // for/else of nuts.py:212-220 with an empty range
           for (int d = 0; d < max_depth; ++d) {  // nuts.py:212
             // logbern(log 0.5): log(u) < log(0.5) <=> u < 0.5 (log is monotone; the two can only disagree for the
             // single double adjacent to 0.5)                                                          nuts.py:213
@@ -302,6 +304,8 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
                 sc.vec(tvid(tail, base + 2))[k * G] = g[k];
               }
               reg_edge = dir;
+            } else {
+              reached_max = true;  // the loop runs out: neither a divergence nor a U-turn (nuts.py:218-220)
             }
           }
           // _Tree.stats (nuts.py:419-435)
@@ -368,6 +372,7 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
           srow[LMC_STAT_STEP_SIZE] = exp(da.log_step);
           srow[LMC_STAT_STEP_SIZE_BAR] = exp(da.log_bar);
           srow[LMC_STAT_N_UNIFORMS] = (double)uc;
+          srow[LMC_STAT_REACHED_MAX_TREEDEPTH] = reached_max ? 1.0 : 0.0;
         }
 
         // ---- write the chain's state back (its next transition may run on another SM) ---------------------------

@@ -105,7 +105,8 @@ class FusedTarget:
         return t
 
 
-def _fill_base(a, kind, chains, *, n_trans, iter0, n_tune, params, seeds, tapes, trace, stats, knobs, stream):
+def _fill_base(a, kind, chains, *, n_trans, iter0, n_tune, params, seeds, tapes, trace, stats, knobs, stream,
+               step_size_override=None):
     """Fill an lmc_sampler_args (everything but target / workspace).  Returns the tensors that must outlive the launch."""
     dev = chains.device
     Cn, D = chains.n_chains, chains.ndim
@@ -141,6 +142,11 @@ def _fill_base(a, kind, chains, *, n_trans, iter0, n_tune, params, seeds, tapes,
     assert trace.stride(2) == 1
     a.trace, a.trace_chain_stride, a.trace_draw_stride = trace.data_ptr(), trace.stride(0), trace.stride(1)
     a.stats, a.status = stats.data_ptr(), chains.status.data_ptr()
+    if step_size_override is not None:   # BaseHMC.step_rand result for this call's transitions (base_hmc.py:154-155)
+        step_size_override = torch.as_tensor(step_size_override, dtype=torch.float64, device=dev).contiguous()
+        assert step_size_override.shape == (Cn,), step_size_override.shape
+        a.step_size_override = step_size_override.data_ptr()
+        keep.append(step_size_override)
     knobs = knobs or {}
     a.tune_group = int(knobs.get("group", 0))
     a.tune_smem_vecs = int(knobs.get("smem_vecs", -1))
@@ -159,7 +165,7 @@ def _alloc_outputs(chains, n_trans, trace, stats):
 
 
 def run_transitions(kind, chains, target, *, n_trans, iter0, n_tune, params, seeds=None, tapes=None,
-                    trace=None, stats=None, knobs=None, stream=None, events=None):
+                    trace=None, stats=None, knobs=None, stream=None, events=None, step_size_override=None):
     """Enqueue `n_trans` transitions of every chain (lmc_nuts_sample / lmc_hmc_sample).  Returns (trace, stats)
     device tensors [C, n_trans, D] and [C, n_trans, NSTATS].  Asynchronous on the current CUDA stream.
     `events`: optional pair of torch.cuda.Event recorded on the launching stream immediately around the library call
@@ -171,7 +177,8 @@ def run_transitions(kind, chains, target, *, n_trans, iter0, n_tune, params, see
     a = L.SamplerArgs()
     with torch.cuda.device(dev):
         keep = _fill_base(a, kind, chains, n_trans=n_trans, iter0=iter0, n_tune=n_tune, params=params, seeds=seeds,
-                          tapes=tapes, trace=trace, stats=stats, knobs=knobs, stream=stream)
+                          tapes=tapes, trace=trace, stats=stats, knobs=knobs, stream=stream,
+                          step_size_override=step_size_override)
         a.target = target.c_struct(dev)
         nbytes = lib.lmc_workspace_bytes(kind, Cn, D, a.max_treedepth, a.tune_group)
         if nbytes < 0:
@@ -221,7 +228,7 @@ class CallbackRun:
     around a user gradient callback.  The loop body (callback + advance) can be captured in a CUDA graph."""
 
     def __init__(self, kind, chains, callback, *, n_trans, iter0, n_tune, params, seeds=None, tapes=None, trace=None,
-                 stats=None, stream=None):
+                 stats=None, stream=None, step_size_override=None):
         self.lib = L.load()
         self.kind, self.chains, self.callback = kind, chains, callback
         dev, Cn, D = chains.device, chains.n_chains, chains.ndim
@@ -234,7 +241,8 @@ class CallbackRun:
         self.c = L.CallbackArgs()
         with torch.cuda.device(dev):
             self.keep = _fill_base(self.c.base, kind, chains, n_trans=n_trans, iter0=iter0, n_tune=n_tune, params=params,
-                                   seeds=seeds, tapes=tapes, trace=self.trace, stats=self.stats, knobs=None, stream=stream)
+                                   seeds=seeds, tapes=tapes, trace=self.trace, stats=self.stats, knobs=None, stream=stream,
+                                   step_size_override=step_size_override)
             nbytes = self.lib.lmc_callback_state_bytes(kind, Cn, D, self.c.base.max_treedepth)
             if nbytes < 0:
                 L.check(int(nbytes), "lmc_callback_state_bytes")
@@ -313,10 +321,10 @@ class CallbackRun:
 
 
 def run_transitions_callback(kind, chains, callback, *, n_trans, iter0, n_tune, params, seeds=None, tapes=None,
-                             trace=None, stats=None, cuda_graph=False):
+                             trace=None, stats=None, cuda_graph=False, step_size_override=None):
     """Callback-mode counterpart of run_transitions (synchronous: returns when every chain has finished)."""
     run = CallbackRun(kind, chains, callback, n_trans=n_trans, iter0=iter0, n_tune=n_tune, params=params, seeds=seeds,
-                      tapes=tapes, trace=trace, stats=stats)
+                      tapes=tapes, trace=trace, stats=stats, step_size_override=step_size_override)
     run.run(cuda_graph=cuda_graph)
     return run.trace, run.stats
 

@@ -47,10 +47,8 @@ class NUTS(BaseHMC):
         super()._account(stats_dev, n_tune_in_block)
         post = stats_dev[:, n_tune_in_block:, :]
         if post.shape[1]:
-            # nuts.py:218-220: the doubling loop ran out without a divergence or a U-turn.  A U-turn at the last
-            # doubling is indistinguishable in the statistics, so this counts depth == max_treedepth, non-diverging.
-            full = (post[:, :, L.STAT_DEPTH] >= self.max_treedepth) & (post[:, :, L.STAT_DIVERGING] == 0)
-            self._reached_max_treedepth += int(full.sum().item())
+            # nuts.py:218-220: the doubling loop ran out without a divergence or a U-turn (flagged by the kernel)
+            self._reached_max_treedepth += int(post[:, :, L.STAT_REACHED_MAX_TREEDEPTH].sum().item())
 
     def warnings(self):
         """reference nuts.py:226-239."""

@@ -12,6 +12,7 @@ distributed over GPUs.
 """
 import logging
 import os
+from collections import namedtuple
 from collections.abc import Iterable
 
 import numpy as np
@@ -23,6 +24,9 @@ from .nuts import NUTS
 from .quadpotential import QuadPotentialDiagAdapt
 
 _log = logging.getLogger("littlemcmc_b200")
+
+# what the reference's per-draw callback receives (parallel_sampling.py:374; sampling.py:303-308)
+Draw = namedtuple("Draw", ["chain", "is_last", "draw_idx", "tuning", "stats", "point", "warnings"])
 
 
 def _resolve_seeds(random_seed, chains):
@@ -50,6 +54,11 @@ def sample(logp_dlogp_func, model_ndim, draws=1000, tune=1000, step=None, init="
 
     Differences a caller can observe: ``cores``, ``mp_ctx``, ``pickle_backend`` and ``progressbar`` are accepted and
     ignored (chains are a tensor dimension, there are no worker processes); ``start`` may also be ``[chains, ndim]``.
+    ``callback(trace=..., draw=Draw(...))`` is the reference's per-draw hook (sampling.py:303-308): it is called for
+    every (draw, chain) after the block of transitions containing the draw has finished, with ``trace`` the host array
+    being filled (``[chains, draws kept so far.., ndim]``) and ``draw.stats`` the one-element list of that draw's
+    statistics dict; a callback makes the driver wait for every block (no copy/compute overlap).  ``KeyboardInterrupt``
+    stops the run and returns the transitions finished so far, like the reference's sequential path (:470-478).
     Extra keywords: ``device`` (CUDA device, default current), ``block`` (transitions per launch, default: sized so a
     trace block is <= 128 MiB), ``return_device`` (keep results as torch tensors on the GPU and skip the host copy),
     ``host_write``: how kept draws reach the pinned host trace -- ``"copy"`` (default): double-buffered device blocks
@@ -113,50 +122,68 @@ def sample(logp_dlogp_func, model_ndim, draws=1000, tune=1000, step=None, init="
     bufs, copy_done = [None, None], [None, None]      # double-buffered device blocks of the trace
     stats_blocks = []
     done, blk = 0, 0
-    while done < T:
-        n = min(block, T - done)
-        if done < keep_from < done + n:
-            n = keep_from - done                       # a block never straddles the discard boundary
-        kept = done >= keep_from
-        if kept and return_device:
-            tr_view = trace_out[:, done - keep_from:done - keep_from + n]
-            _, st = step._run(n, int(tune), trace=tr_view)
-        elif kept and direct:
-            # the kernel writes trace[:, i] = q (sampling.py:513) into the caller-visible pinned array itself
-            tr_view = host_trace[:, done - keep_from:done - keep_from + n]
-            _, st = step._run(n, int(tune), trace=tr_view)
-        else:
-            i = blk & 1
-            if bufs[i] is None:
-                bufs[i] = torch.empty(chains, min(block, T), D, dtype=torch.float64, device=dev)
-            if copy_done[i] is not None:
-                compute.wait_event(copy_done[i])       # the previous copy out of this buffer must have finished
-            tr_view = bufs[i][:, :n]
-            _, st = step._run(n, int(tune), trace=tr_view)
-            if kept:
-                ready = torch.cuda.Event()
-                ready.record(compute)
-                copy_stream.wait_event(ready)
-                dst = host_trace[:, done - keep_from:done - keep_from + n]
-                # [chains] rows of n*D contiguous doubles each, different pitches on the two sides
-                L.check(L.load().lmc_memcpy2d_d2h(dst.data_ptr(), dst.stride(0) * 8, tr_view.data_ptr(),
-                                                  tr_view.stride(0) * 8, n * D * 8, chains,
-                                                  copy_stream.cuda_stream), "lmc_memcpy2d_d2h")
-                copy_done[i] = torch.cuda.Event()
-                copy_done[i].record(copy_stream)
-        stats_blocks.append(st)
-        done += n
-        blk += 1
+    interrupted = False
+    try:
+        while done < T:
+            n = min(block, T - done)
+            if done < keep_from < done + n:
+                n = keep_from - done                       # a block never straddles the discard boundary
+            kept = done >= keep_from
+            if kept and return_device:
+                tr_view = trace_out[:, done - keep_from:done - keep_from + n]
+                _, st = step._run(n, int(tune), trace=tr_view)
+            elif kept and direct:
+                # the kernel writes trace[:, i] = q (sampling.py:513) into the caller-visible pinned array itself
+                tr_view = host_trace[:, done - keep_from:done - keep_from + n]
+                _, st = step._run(n, int(tune), trace=tr_view)
+            else:
+                i = blk & 1
+                if bufs[i] is None:
+                    bufs[i] = torch.empty(chains, min(block, T), D, dtype=torch.float64, device=dev)
+                if copy_done[i] is not None:
+                    compute.wait_event(copy_done[i])       # the previous copy out of this buffer must have finished
+                tr_view = bufs[i][:, :n]
+                _, st = step._run(n, int(tune), trace=tr_view)
+                if kept:
+                    ready = torch.cuda.Event()
+                    ready.record(compute)
+                    copy_stream.wait_event(ready)
+                    dst = host_trace[:, done - keep_from:done - keep_from + n]
+                    # [chains] rows of n*D contiguous doubles each, different pitches on the two sides
+                    L.check(L.load().lmc_memcpy2d_d2h(dst.data_ptr(), dst.stride(0) * 8, tr_view.data_ptr(),
+                                                      tr_view.stride(0) * 8, n * D * 8, chains,
+                                                      copy_stream.cuda_stream), "lmc_memcpy2d_d2h")
+                    copy_done[i] = torch.cuda.Event()
+                    copy_done[i].record(copy_stream)
+            stats_blocks.append(st)
+            if callback is not None:
+                compute.synchronize()
+                copy_stream.synchronize()
+                _per_draw_callbacks(callback, step, st, tr_view, host_trace, done, n, T, int(tune), keep_from)
+            done += n
+            blk += 1
+    except KeyboardInterrupt:                              # sampling.py:470-478: return what has been sampled so far
+        interrupted = True
+        _log.warning("Interrupted after %d of %d transitions.", done, T)
     _mark("enqueue")
     compute.synchronize()
     _mark("compute_sync")
     copy_stream.synchronize()
     _mark("copy_sync")
     step._check_status()
-    if tune < T:
+    if tune < done:
         step.stop_tuning()                                                          # sampling.py:510-511
+    if interrupted:                                                                 # keep the finished transitions only
+        n_keep = max(0, done - keep_from)
+        if return_device:
+            trace_out = trace_out[:, :n_keep]
+        else:
+            host_trace = host_trace[:, :n_keep]
+    if not stats_blocks:
+        stats_blocks = [torch.empty(chains, 0, L.NSTATS, dtype=torch.float64, device=dev)]
     stats_dev = torch.cat(stats_blocks, 1) if len(stats_blocks) > 1 else stats_blocks[0]
-    step._account(stats_dev, int(tune))
+    stats_dev = stats_dev[:, :done]                     # an interrupted block's statistics are dropped with its draws
+    step._account(stats_dev, min(int(tune), done))
 
     _mark("account")
     stats_kept = stats_dev[:, keep_from:]
@@ -176,6 +203,19 @@ def sample(logp_dlogp_func, model_ndim, draws=1000, tune=1000, step=None, init="
         stats[name] = plane if np.dtype(dtype) == np.float64 else plane.astype(dtype)
     _mark("stats_to_host")
     return host_trace.numpy(), stats
+
+
+def _per_draw_callbacks(callback, step, st_dev, tr_dev_or_host, host_trace, first, n, T, tune, keep_from):
+    """Call the reference-style hook once per (draw, chain) of a finished block (sampling.py:303-308)."""
+    st = st_dev.cpu().numpy()
+    pts = tr_dev_or_host.cpu().numpy() if tr_dev_or_host.is_cuda else tr_dev_or_host.numpy()
+    trace_np = None if host_trace is None else host_trace.numpy()
+    dtypes = step.stats_dtypes[0]
+    for j in range(n):
+        idx = first + j
+        for c in range(st.shape[0]):
+            sd = {name: np.asarray(st[c, j, step._stat_columns[name]]).astype(dt)[()] for name, dt in dtypes.items()}
+            callback(trace=trace_np, draw=Draw(c, idx == T - 1, idx, idx < tune, [sd], pts[c, j], None))
 
 
 def init_nuts(logp_dlogp_func, model_ndim, init="auto", random_seed=None, **kwargs):

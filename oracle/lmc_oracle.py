@@ -393,6 +393,7 @@ def nuts_transition(f: LogpFunc, pot: DiagPotential, start: State, step_size: fl
         if turn or turn1 or turn2:                                                         # :340
             turning = True
             break
+    reached_max = not (diverging or turning)                   # the for/else of nuts.py:212-220 (counted at :219-220)
 
     mean_tree_accept = 0.0                                     # :280
     if log_size > 0:                                           # :421-425
@@ -405,6 +406,7 @@ def nuts_transition(f: LogpFunc, pot: DiagPotential, start: State, step_size: fl
         "tree_size": n_prop,
         "max_energy_error": max_dE,
         "model_logp": prop.model_logp,
+        "reached_max_treedepth": reached_max,                  # not a reference statistic: NUTS._reached_max_treedepth += 1
     }                                                          # :427-435
     return prop, stats, diverging
 
@@ -465,6 +467,8 @@ class Sampler:
     max_steps: int = 1024
     tune: bool = True
     iter_count: int = 0
+    step_rand: Optional[Callable[[float], float]] = None       # base_hmc.py:43,154-155
+    reached_max_treedepth: int = 0                             # nuts.py:202,219-220
     step_adapt: DualAverage = field(init=False)
 
     def __post_init__(self):
@@ -485,12 +489,16 @@ class Sampler:
             raise ValueError("Bad initial energy: {}. The model might be misspecified.".format(start.energy))
         adapt_step = self.tune and self.adapt_step_size                                # :151
         step_size = self.step_adapt.current(adapt_step)                                # :152
+        if self.step_rand is not None:
+            step_size = self.step_rand(step_size)                                      # :154-155
         self.step_size = step_size
         if self.kind == "nuts":
             early = self.tune and self.iter_count < 200                                # nuts.py:205-208
             depth_cap = self.early_max_treedepth if early else self.max_treedepth
             end, st, diverging = nuts_transition(self.f, self.pot, start, step_size, self.Emax, depth_cap, rng)
             accept_stat = st["mean_tree_accept"]
+            if st["reached_max_treedepth"] and not self.tune:                          # nuts.py:218-220
+                self.reached_max_treedepth += 1
         else:
             end, st, diverging = hmc_transition(self.f, self.pot, start, step_size, self.Emax,
                                                 self.path_length, self.max_steps, rng)

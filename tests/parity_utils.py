@@ -9,10 +9,11 @@ from oracle import lmc_oracle as orc
 from tests import golden_cases as gc
 
 NUTS_STATS = {"depth": 0, "tree_size": 1, "mean_tree_accept": 2, "energy": 3, "energy_error": 4,
-              "max_energy_error": 5, "model_logp": 6, "diverging": 7, "tune": 8, "step_size": 9, "step_size_bar": 10}
+              "max_energy_error": 5, "model_logp": 6, "diverging": 7, "tune": 8, "step_size": 9, "step_size_bar": 10,
+              "reached_max_treedepth": 12}
 HMC_STATS = {"n_steps": 0, "path_length": 1, "accept": 2, "energy": 3, "energy_error": 4, "accepted": 5,
              "model_logp": 6, "diverging": 7, "tune": 8, "step_size": 9, "step_size_bar": 10}
-EXACT = ("depth", "tree_size", "diverging", "tune", "n_steps", "accepted")
+EXACT = ("depth", "tree_size", "diverging", "tune", "n_steps", "accepted", "reached_max_treedepth")
 
 
 @dataclass
@@ -60,12 +61,13 @@ def oracle_run(case):
     """
     D, kind = int(case["ndim"]), str(case["kind"])
     T, tune = int(case["tune"]) + int(case["draws"]), int(case["tune"])
-    names = orc.NUTS_STAT_NAMES if kind == "nuts" else orc.HMC_STAT_NAMES
+    # + the flag behind NUTS._reached_max_treedepth (nuts.py:218-220), which the kernels report per transition
+    names = orc.NUTS_STAT_NAMES + ("reached_max_treedepth",) if kind == "nuts" else orc.HMC_STAT_NAMES
     recs, tapes, stats_all = [], [], []
     for s in case["seeds"]:
         rng = orc.TapeRecorder(np.random.RandomState(int(s)))
         smp = orc.Sampler(gc.target_fn(case)(), D, orc.DiagPotential(D, **gc.potential_kw(case)), kind=kind,
-                          **gc.sampler_kw(case))
+                          step_rand=case.get("step_rand"), **gc.sampler_kw(case))
         # sampling.py:503-513, spelled out so the state can be snapshotted around each _astep
         smp.tune = bool(tune)
         smp.reset_tuning()
@@ -219,8 +221,13 @@ def gpu_run_transitionwise(case, ora, knobs=None, device="cuda:0", callback=None
         for i, buf in enumerate((ch.mean_fg, ch.rawvar_fg, ch.mean_bg, ch.rawvar_bg)):
             buf[:, :D] = pre["welford"][:, t, i]
         ch.adapt[:, :9] = pre["adapt"][:, t]
+        extra = {}
+        if case.get("step_rand") is not None:   # base_hmc.py:154-155: the hook's output replaces current()
+            tuning = t < int(case["tune"]) and bool(params["adapt_step_size"])
+            cur = np.exp(ora["pre"]["adapt"][:, t, L.ADAPT_LOG_STEP if tuning else L.ADAPT_LOG_BAR])
+            extra["step_size_override"] = np.array([case["step_rand"](float(e)) for e in cur])
         _, st = _launch(case, ch, tgt, callback, n_trans=1, iter0=t, n_tune=int(case["tune"]), params=params,
-                        tapes=(normals_d[:, t:t + 1], uniforms_d[:, t:t + 1]), knobs=knobs)
+                        tapes=(normals_d[:, t:t + 1], uniforms_d[:, t:t + 1]), knobs=knobs, **extra)
         q, var, wel, ad = _read_state(ch)
         out_q.append(q); out_var.append(var); out_wel.append(wel); out_ad.append(ad)  # noqa: E702
         out_st.append(st[:, 0].cpu().numpy())
@@ -229,12 +236,14 @@ def gpu_run_transitionwise(case, ora, knobs=None, device="cuda:0", callback=None
 
 
 def run_case_on_gpu_and_oracle(name, n_trans=None, knobs=None, device="cuda:0", chained=False,
-                               chunks=1, callback=None) -> ParityResult:
+                               chunks=1, callback=None, overrides=None) -> ParityResult:
     """`callback`: None = fused kernels; "torch" / "torch-graph" = callback mode with the case's density as a batched
     torch op (eager / CUDA graph); "numpy" = callback mode with the oracle's per-chain NumPy callable."""
     from littlemcmc_b200 import _lib as L
     case, _ = gc.load(name)
     case = truncate_case(case, n_trans)
+    if overrides:                       # e.g. max_treedepth=3, step_rand=callable: variations on a committed fixture
+        case = dict(case, **overrides)
     ora = oracle_run(case)
     table = NUTS_STATS if str(case["kind"]) == "nuts" else HMC_STATS
     if callback in ("torch", "torch-graph"):

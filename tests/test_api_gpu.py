@@ -225,3 +225,63 @@ def test_philox_mode_equals_tape_mode():
     normals, _ = engine.rng_fill(engine.seeds_tensor(np.arange(64), "cuda:0"), 1000, 0, 8, 4)
     z = normals.cpu().numpy().ravel()
     assert abs(z.mean()) < 0.01 and abs(z.std() - 1) < 0.01
+
+
+def test_per_draw_callback_and_interrupt():
+    """reference sampling.py:303-308 (per-draw `callback(trace=, draw=)`) and :470-478 (KeyboardInterrupt returns the
+    transitions sampled so far)."""
+    lmc = _lmc()
+    D, chains, tune, draws = 5, 3, 6, 9
+    target = lmc.targets.DiagGaussian(sigma=np.linspace(0.5, 2, D))
+    seen = []
+
+    def cb(trace, draw):
+        seen.append((draw.draw_idx, draw.chain, draw.tuning, draw.is_last, draw.point.copy(), draw.stats[0]["tree_size"]))
+
+    kw = dict(model_ndim=D, draws=draws, tune=tune, chains=chains, start=np.full(D, 0.1), random_seed=[1, 2, 3],
+              discard_tuned_samples=False, block=4)
+    trace, stats = lmc.sample(target, callback=cb, **kw)
+    assert len(seen) == chains * (tune + draws)
+    assert [s[0] for s in seen] == sorted(s[0] for s in seen)            # draws arrive in order
+    for idx, c, tuning, last, point, tree_size in seen:
+        assert tuning == (idx < tune) and last == (idx == tune + draws - 1)
+        assert np.array_equal(point, trace[c, idx])
+        assert tree_size == stats["tree_size"][c, idx, 0]
+    ref_trace, _ = lmc.sample(target, **kw)
+    assert np.array_equal(trace, ref_trace)                              # the hook does not change the chains
+
+    def stop_at_9(trace, draw):
+        if draw.draw_idx == 9:
+            raise KeyboardInterrupt
+
+    part, pstats = lmc.sample(target, callback=stop_at_9, **kw)
+    assert part.shape == (chains, 8, D) and pstats["depth"].shape == (chains, 8, 1)   # two finished blocks of 4
+    assert np.array_equal(part, ref_trace[:, :8])
+
+
+def test_step_rand_through_the_api():
+    """reference base_hmc.py:154-155.  The hook sees the step sizes of all chains as one array (or, if it cannot take
+    an array, one chain at a time) and the chain integrates with what it returns."""
+    lmc = _lmc()
+    D, chains = 7, 4
+    target = lmc.targets.DiagGaussian(sigma=np.linspace(0.5, 2, D))
+    calls = []
+
+    def vec_hook(eps):
+        calls.append(np.shape(eps))
+        return eps * 0.5
+
+    def scalar_hook(eps):
+        return float(eps) * 0.5      # float() of a 4-vector raises: the per-chain fallback is used
+
+    out = []
+    for hook in (vec_hook, scalar_hook, None):
+        pot = lmc.QuadPotentialDiagAdapt(D, np.zeros(D), np.ones(D), 10)
+        step = lmc.NUTS(target, D, potential=pot, step_rand=hook)
+        out.append(lmc.sample(target, D, draws=5, tune=10, step=step, chains=chains, start=np.full(D, 0.1),
+                              random_seed=[4, 5, 6, 7], discard_tuned_samples=False))
+    assert calls and all(c == (chains,) for c in calls) and len(calls) == 15
+    assert np.array_equal(out[0][0], out[1][0])                          # both calling conventions agree
+    assert not np.array_equal(out[0][0], out[2][0])                      # and the hook matters
+    # halving every step size lengthens the trees
+    assert out[0][1]["tree_size"].mean() > out[2][1]["tree_size"].mean()

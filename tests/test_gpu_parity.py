@@ -78,3 +78,29 @@ def test_d1000_shapes(group):
     res = pu.run_case_on_gpu_and_oracle("nuts_illcond_d1000", knobs=dict(group=group))
     print(pu.parity_report(res))
     pu.assert_parity(res, rtol=RTOL)
+
+
+@pytest.mark.parametrize("callback", [None, "torch"])
+def test_reached_max_treedepth_flag(callback):
+    """The for/else of nuts.py:212-220 (tree loop exhausted without divergence or U-turn, what
+    NUTS._reached_max_treedepth counts) with a tree depth cap low enough to be hit often."""
+    res = pu.run_case_on_gpu_and_oracle("nuts_diag_d37", n_trans=40, callback=callback,
+                                        overrides=dict(max_treedepth=2, early_max_treedepth=2))
+    pu.assert_parity(res, rtol=RTOL)
+    hits = res.cpu_stats["reached_max_treedepth"]
+    assert 0 < hits.sum() < hits.size, "the case must exercise both outcomes"
+    # a transition that stopped at the cap by a U-turn has depth == cap but is NOT counted (statistics alone cannot
+    # tell the two apart, the kernel's flag can)
+    at_cap = (res.cpu_stats["depth"] == 2) & (res.cpu_stats["diverging"] == 0)
+    assert (at_cap & (hits == 0)).any()
+
+
+@pytest.mark.parametrize("callback", [None, "torch"])
+def test_step_rand_hook(callback):
+    """BaseHMC.step_rand (base_hmc.py:154-155): the step size every transition integrates with is the hook's output,
+    while dual averaging keeps adapting its own state."""
+    jitter = lambda eps: eps * 0.8 + 0.01   # noqa: E731  (deterministic so both sides see the same numbers)
+    res = pu.run_case_on_gpu_and_oracle("nuts_diag_d37", n_trans=30, callback=callback, overrides=dict(step_rand=jitter))
+    pu.assert_parity(res, rtol=RTOL)
+    plain = pu.run_case_on_gpu_and_oracle("nuts_diag_d37", n_trans=30, callback=callback)
+    assert not np.array_equal(res.gpu_trace, plain.gpu_trace)
