@@ -222,6 +222,118 @@ class DiagPotential:
 
 
 # --------------------------------------------------------------------------------------------------
+# dense potentials  (reference quadpotential.py:390-615), float64 throughout
+# --------------------------------------------------------------------------------------------------
+class FullPotential:
+    """``QuadPotentialFull``: static dense covariance (reference quadpotential.py:430-468)."""
+    adapt = False
+
+    def __init__(self, cov):
+        import scipy.linalg
+        self.cov = np.array(cov, dtype="d")                                  # :445
+        self.chol = scipy.linalg.cholesky(self.cov, lower=True)               # :446
+        self.n = len(self.cov)
+
+    def velocity(self, p):                                                    # :449-451
+        return np.dot(self.cov, p)
+
+    def random(self, rng):                                                    # :453-456
+        import scipy.linalg
+        vals = rng.normal(size=self.n)
+        return scipy.linalg.solve_triangular(self.chol.T, vals)
+
+    def update(self, sample, tune):
+        pass
+
+    def reset(self):                                                          # base class: no-op (:138-140)
+        pass
+
+
+class FullInvPotential(FullPotential):
+    """``QuadPotentialFullInv``: static dense inverse covariance A (reference quadpotential.py:390-427)."""
+
+    def __init__(self, A):
+        import scipy.linalg
+        self.A = np.array(A, dtype="d")
+        self.L = scipy.linalg.cholesky(self.A, lower=True)                    # :405
+        self.n = len(self.A)
+
+    def velocity(self, p):                                                    # :407-412
+        import scipy.linalg
+        return scipy.linalg.cho_solve((self.L, True), p)
+
+    def random(self, rng):                                                    # :414-417
+        return np.dot(self.L, rng.normal(size=self.n))
+
+
+class WelfordCov:
+    """``_WeightedCovariance`` (reference quadpotential.py:573-615)."""
+
+    def __init__(self, n, initial_mean=None, initial_covariance=None, initial_weight=0.0):
+        self.n_samples = float(initial_weight)
+        self.mean = np.zeros(n) if initial_mean is None else np.array(initial_mean, dtype="d")
+        self.raw_cov = np.eye(n) if initial_covariance is None else np.array(initial_covariance, dtype="d")
+        self.raw_cov = self.raw_cov * self.n_samples                          # :600
+
+    def add_sample(self, x, weight=1):                                        # :607-613
+        x = np.asarray(x, dtype="d")
+        self.n_samples += 1
+        old_diff = x - self.mean
+        self.mean = self.mean + old_diff / self.n_samples
+        new_diff = x - self.mean
+        self.raw_cov = self.raw_cov + weight * new_diff[:, None] * old_diff[None, :]
+
+    def current_covariance(self):                                             # :615-621
+        if self.n_samples == 0:
+            raise ValueError("Can not compute covariance without samples.")
+        return self.raw_cov / (self.n_samples - 1)
+
+
+class FullAdaptPotential(FullPotential):
+    """``QuadPotentialFullAdapt`` (reference quadpotential.py:471-570).  The reference never resets this potential
+    between chains (base-class ``reset`` is a no-op, :138-140); ``reset`` here does nothing either, so a fresh object
+    per chain is what gives every chain the same initial mass matrix."""
+    adapt = True
+
+    def __init__(self, n, initial_mean, initial_cov=None, initial_weight=0, adaptation_window=101,
+                 adaptation_window_multiplier=2, update_window=1):
+        import scipy.linalg
+        if initial_cov is None:                                               # :500-502
+            initial_cov, initial_weight = np.eye(n), 1
+        self.n = int(n)
+        self.cov = np.array(initial_cov, dtype="d")
+        self.chol = scipy.linalg.cholesky(self.cov, lower=True)
+        self.chol_error = None
+        self.fg = WelfordCov(self.n, initial_mean, initial_cov, initial_weight)
+        self.bg = WelfordCov(self.n)
+        self.n_samples = 0
+        self.adaptation_window = int(adaptation_window)
+        self.adaptation_window_multiplier = float(adaptation_window_multiplier)
+        self.update_window = int(update_window)
+        self.previous_update = 0
+
+    def update(self, sample, tune):                                           # :528-554
+        import scipy.linalg
+        if not tune:
+            return
+        delta = self.n_samples - self.previous_update
+        self.fg.add_sample(sample, weight=1)
+        self.bg.add_sample(sample, weight=1)
+        if (delta + 1) % self.update_window == 0:                             # :540-541 -> :520-526
+            self.cov = self.fg.current_covariance()
+            try:
+                self.chol = scipy.linalg.cholesky(self.cov, lower=True)
+            except (scipy.linalg.LinAlgError, ValueError) as error:
+                self.chol_error = error
+        if delta >= self.adaptation_window:                                   # :545-552
+            self.fg = self.bg
+            self.bg = WelfordCov(self.n)
+            self.previous_update = self.n_samples
+            self.adaptation_window = int(self.adaptation_window * self.adaptation_window_multiplier)
+        self.n_samples += 1
+
+
+# --------------------------------------------------------------------------------------------------
 # dual averaging  (reference step_sizes.py:23-99)
 # --------------------------------------------------------------------------------------------------
 class DualAverage:
@@ -542,6 +654,17 @@ def diag_gaussian(tau: np.ndarray) -> LogpFunc:
 
     def f(q):
         g = -(tau * q)
+        return 0.5 * np.dot(q, g), g
+
+    return f
+
+
+def dense_gaussian(prec: np.ndarray) -> LogpFunc:
+    """logp = -1/2 q' P q with a dense precision matrix P;  g = -(P q), logp = 0.5 * q.g"""
+    prec = np.asarray(prec, dtype="d")
+
+    def f(q):
+        g = -np.dot(prec, q)
         return 0.5 * np.dot(q, g), g
 
     return f

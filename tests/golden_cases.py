@@ -7,7 +7,9 @@ import numpy as np
 from oracle import lmc_oracle as orc
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASE_NAMES = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+_ALL = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+CASE_NAMES = [n for n in _ALL if not n.startswith("dense_")]          # diagonal potentials (make_golden.py)
+DENSE_CASE_NAMES = [n for n in _ALL if n.startswith("dense_")]        # dense potentials (make_golden_dense.py)
 
 _SAMPLER_KEYS = ("max_treedepth", "early_max_treedepth", "Emax", "path_length", "max_steps", "step_scale",
                  "adapt_step_size", "target_accept")
@@ -22,6 +24,8 @@ def load(name):
 
 
 def target_fn(case):
+    if case["target"] == "dense_gaussian":
+        return lambda: orc.dense_gaussian(case["prec"])
     if case["target"] == "diag_gaussian":
         return lambda: orc.diag_gaussian(case["tau"])
     if case["target"] == "funnel":
@@ -34,6 +38,32 @@ def potential_kw(case):
         return dict(var=case["pot_var"], initial_mean=case["pot_mean"], initial_weight=float(case["pot_weight"]),
                     adapt=True)
     return dict(var=case["pot_var"], adapt=False)
+
+
+def dense_potential(case):
+    """A fresh oracle potential for one chain of a dense case."""
+    if case["pot"] == "full":
+        return orc.FullPotential(case["pot_matrix"])
+    if case["pot"] == "fullinv":
+        return orc.FullInvPotential(case["pot_matrix"])
+    return orc.FullAdaptPotential(int(case["ndim"]), case["pot_mean"], case["pot_matrix"], float(case["pot_weight"]),
+                                  adaptation_window=int(case["adaptation_window"]),
+                                  adaptation_window_multiplier=float(case["adaptation_window_multiplier"]))
+
+
+def run_oracle_dense(case, record=False):
+    """Every chain with a fresh potential (see tests/golden/make_golden_dense.py).  -> trace [C,T,D], stats, pots"""
+    D, kind = int(case["ndim"]), str(case["kind"])
+    traces, stats_all, pots = [], [], []
+    for s in case["seeds"]:
+        pot = dense_potential(case)
+        smp = orc.Sampler(target_fn(case)(), D, pot, kind=kind, **sampler_kw(case))
+        tr, st = orc.sample_chain(smp, case["start"], int(case["draws"]), int(case["tune"]),
+                                  np.random.RandomState(int(s)))
+        traces.append(tr)
+        stats_all.append(st)
+        pots.append((pot, smp))
+    return np.stack(traces), {n: np.stack([s[n] for s in stats_all]) for n in stats_all[0]}, pots
 
 
 def sampler_kw(case):

@@ -59,3 +59,27 @@ def test_final_adaptation_state_matches_reference():
         np.testing.assert_allclose([sa.log_step, sa.log_bar, sa.hbar, sa.count, sa.mu],
                                    ref["final_step_adapt"][c], rtol=RTOL)
         assert smp.pot.n_samples == int(ref["final_n_samples"][c]) == int(case["tune"])
+
+
+@pytest.mark.parametrize("name", gc.DENSE_CASE_NAMES)
+def test_dense_oracle_matches_reference(name):
+    """Dense potentials (reference quadpotential.py:390-615): QuadPotentialFull / FullInv / FullAdapt.  The matrix
+    products run through BLAS on both sides (dgemv / dtrsv / dpotrf), hence the slightly wider float tolerance."""
+    case, ref = gc.load(name)
+    trace, stats, pots = gc.run_oracle_dense(case)
+    assert trace.shape == ref["trace"].shape
+    for k, v in stats.items():
+        r = ref["stat_" + k]
+        if k in gc.EXACT_STATS:
+            assert np.array_equal(v, r), k
+        else:
+            np.testing.assert_allclose(v, r, rtol=1e-10, atol=1e-300, err_msg=k)
+    np.testing.assert_allclose(trace, ref["trace"], rtol=1e-10, atol=1e-300)
+    for c, (pot, smp) in enumerate(pots):
+        sa = smp.step_adapt
+        np.testing.assert_allclose([sa.log_step, sa.log_bar, sa.hbar, sa.count, sa.mu], ref["final_step_adapt"][c],
+                                   rtol=1e-10)
+        if case["pot"] == "fulladapt":
+            np.testing.assert_allclose(pot.cov, ref["final_cov"][c], rtol=1e-10)
+            assert pot.n_samples == int(ref["final_n_samples"][c]) == int(case["tune"])
+            assert pot.adaptation_window == int(ref["final_window"][c])
