@@ -235,6 +235,71 @@ int lmc_callback_begin(int32_t kind, const lmc_callback_args* args);
  * integration.py:105-112). */
 int lmc_callback_advance(int32_t kind, const lmc_callback_args* args);
 
+/*
+ * Dense-mass mode: transitions with a DENSE mass matrix -- QuadPotentialFull / QuadPotentialFullInv /
+ * QuadPotentialFullAdapt (quadpotential.py:390-615).  With a dense matrix three things are batched operations over
+ * chains that cannot live inside one chain's thread group: the gradient (as in callback mode), the velocity
+ * v = M^-1 p (velocity(): a matrix-vector product per chain, :407-412, :449-451), and the momentum draw
+ * p0 = potential.random() (a triangular solve / product with the Cholesky factor, :414-417, :453-456); an adaptive
+ * matrix is also updated outside (update(): rank-1 covariance update + Cholesky, :528-554).  The state machine is the
+ * callback-mode one with more evaluation points; after every lmc_dense_advance each chain publishes in need[chain]
+ * which results it waits for, the caller computes them for those chains and calls advance again:
+ *
+ *   LMC_NEED_UPDATE  potential.update(q[chain]) -- the transition that just ended was a tuning one (do this first)
+ *   LMC_NEED_MOM     p0_eval[chain]   = potential.random() with the standard normals n_eval[chain]
+ *   LMC_NEED_GRAD    logp_eval[chain], g_eval[chain] = logp_dlogp_func(q_eval[chain])
+ *   LMC_NEED_VEL     v_eval[chain, r] = velocity(x_eval[chain, r]) for r = 0 (a momentum) and r = 1 (a gradient)
+ *
+ * One leapfrog costs one gradient and one two-vector velocity evaluation: the velocity at the half-kicked momentum
+ * p + dt g (integration.py:108-111) is formed as velocity(p) + dt velocity(g) -- velocity() is linear, so this is the
+ * same vector up to rounding -- which is why every state carries w = velocity(g) next to v = velocity(p).  Stack
+ * entries and trajectory edges store their velocities (a dense velocity cannot be recomputed in place).  Everything
+ * else in `base` means what it means for lmc_nuts_sample; base.var, the Welford arrays, base.target and
+ * base.workspace are ignored; dual averaging of the step size stays inside the kernel.
+ */
+#define LMC_NEED_GRAD 1
+#define LMC_NEED_VEL 2
+#define LMC_NEED_MOM 4
+#define LMC_NEED_UPDATE 8
+
+typedef struct lmc_dense_args {
+  lmc_sampler_args base;
+  double* q_eval;          /* [n_chains, ld]    out: position the gradient is needed at (padding = 0)              */
+  const double* g_eval;    /* [n_chains, ld]    in                                                                 */
+  const double* logp_eval; /* [n_chains]        in                                                                 */
+  double* x_eval;          /* [n_chains, 2, ld] out: momentum (row 0) and gradient (row 1) whose velocity is needed */
+  const double* v_eval;    /* [n_chains, 2, ld] in : velocity(x_eval rows)                                         */
+  double* n_eval;          /* [n_chains, ld]    out: standard normals of the next momentum draw                    */
+  const double* p0_eval;   /* [n_chains, ld]    in : potential.random() for those normals                          */
+  int32_t* need;           /* [n_chains]        out: OR of LMC_NEED_* the chain waits for (0: finished)            */
+  void* machine;           /* >= lmc_dense_state_bytes(...) bytes, 16-byte aligned, owned by the caller            */
+  int64_t machine_bytes;
+  int32_t* n_running;      /* device counter: chains that have not finished                                        */
+} lmc_dense_args;
+
+int64_t lmc_dense_state_bytes(int32_t kind, int32_t n_chains, int32_t ndim, int32_t max_treedepth);
+/* Start base.n_trans transitions of every chain (need = GRAD | MOM everywhere). */
+int lmc_dense_begin(int32_t kind, const lmc_dense_args* args);
+/* Consume what each chain asked for and run it to its next evaluation point. */
+int lmc_dense_advance(int32_t kind, const lmc_dense_args* args);
+
+/* y[c, r, :] = A_c x[c, r, :] for the `n_idx` chains c = idx[i] (idx == NULL: chains 0..n_idx-1) and r < nrhs (1 or
+ * 2): QuadPotentialFull(Adapt).velocity (quadpotential.py:449-451), the HBM-bound operation of dense-mass sampling
+ * (8 D^2 bytes of matrix per chain and call; both right-hand sides share one pass over it).  A_c = A + c *
+ * chain_stride (elements; 0 = one matrix shared by all chains), row-major [ndim, lda], lda even, 16-byte aligned.
+ * x and y are [n_chains, nrhs, ld]. */
+int lmc_dense_matvec(const int32_t* idx, int32_t n_idx, const double* A, int64_t chain_stride, int64_t lda,
+                     int32_t ndim, int64_t ld, const double* x, double* y, int32_t nrhs, void* stream);
+
+/* _WeightedCovariance.add_sample (quadpotential.py:607-613) on the foreground and background estimators of the
+ * chains idx[0..n_idx): n_samples += 1; mean += (x - mean) / n_samples; raw_cov += new_diff old_diff^T; then
+ * cov = raw_cov_fg / (n_samples_fg - 1) (current_covariance, :615-621 via _update_from_weightvar, :520-526).
+ * x: [n_chains, ld] (the chains' positions); mean_*: [n_chains, ld]; raw_*, cov: [n_chains, ndim, lda];
+ * nsamp: [n_chains, 2] float64 (fg, bg), updated in place.  cov == NULL skips the refresh (update_window > 1). */
+int lmc_dense_cov_update(const int32_t* idx, int32_t n_idx, int32_t ndim, int64_t ld, int64_t lda, const double* x,
+                         double* mean_fg, double* raw_fg, double* mean_bg, double* raw_bg, double* nsamp, double* cov,
+                         void* stream);
+
 /* Dump the numbers the PHILOX mode would consume into tapes (tests: Philox path == tape path == oracle).
  * normals: [n_chains, n_trans, ndim]; uniforms: [n_chains, n_trans, u_stride]. */
 int lmc_rng_fill(const uint64_t* seeds, int32_t n_chains, int32_t ndim, int64_t iter0, int32_t n_trans,

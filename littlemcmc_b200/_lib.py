@@ -58,6 +58,14 @@ class CallbackArgs(C.Structure):
                 ("machine", C.c_void_p), ("machine_bytes", C.c_int64), ("n_running", C.c_void_p)]
 
 
+class DenseArgs(C.Structure):
+    _fields_ = [("base", SamplerArgs), ("q_eval", C.c_void_p), ("g_eval", C.c_void_p), ("logp_eval", C.c_void_p),
+                ("x_eval", C.c_void_p), ("v_eval", C.c_void_p), ("n_eval", C.c_void_p), ("p0_eval", C.c_void_p),
+                ("need", C.c_void_p), ("machine", C.c_void_p), ("machine_bytes", C.c_int64), ("n_running", C.c_void_p)]
+
+
+NEED_GRAD, NEED_VEL, NEED_MOM, NEED_UPDATE = 1, 2, 4, 8
+
 # every symbol include/lmc_b200.h declares: (restype, argtypes)
 _P, _I32, _I64 = C.c_void_p, C.c_int32, C.c_int64
 SYMBOLS = {
@@ -68,6 +76,11 @@ SYMBOLS = {
     "lmc_callback_state_bytes": (_I64, [_I32, _I32, _I32, _I32]),
     "lmc_callback_begin": (C.c_int, [_I32, C.POINTER(CallbackArgs)]),
     "lmc_callback_advance": (C.c_int, [_I32, C.POINTER(CallbackArgs)]),
+    "lmc_dense_state_bytes": (_I64, [_I32, _I32, _I32, _I32]),
+    "lmc_dense_begin": (C.c_int, [_I32, C.POINTER(DenseArgs)]),
+    "lmc_dense_advance": (C.c_int, [_I32, C.POINTER(DenseArgs)]),
+    "lmc_dense_matvec": (C.c_int, [_P, _I32, _P, _I64, _I64, _I32, _I64, _P, _P, _I32, _P]),
+    "lmc_dense_cov_update": (C.c_int, [_P, _I32, _I32, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),
     "lmc_compute_state": (C.c_int, [C.POINTER(Target), _I32, _I32, _I64, _P, _P, _P, _I64, _P, _P, _P, _P, _P]),
     "lmc_leapfrog_step": (C.c_int, [C.POINTER(Target), _I32, _I32, _I64, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P,
                                     _P, _P, _P]),

@@ -103,7 +103,20 @@ class BaseHMC:
             override = self._apply_step_rand(self.iter_count < n_tune)
         common = dict(n_trans=n_trans, iter0=self.iter_count, n_tune=n_tune, params=self._params(), seeds=self._seeds,
                       tapes=tapes, trace=trace, stats=stats, step_size_override=override)
-        if fused is not None:
+        if getattr(self.potential, "_dense", False):
+            # dense mass matrix: velocity / momentum draw / matrix update are batched operations next to the gradient
+            cb = self._logp_dlogp_func
+            if fused is not None:            # a built-in density: evaluate it as one torch op over the chains that ask
+                key = str(self._chains.device)
+                if getattr(self, "_dense_cb_key", None) != key:
+                    self._dense_cb, self._dense_cb_key = cb.torch_batched(self._chains.device), key
+                cb = self._dense_cb
+            if events is not None:
+                events[0].record()
+            tr, st = engine.run_transitions_dense(self._kind, self._chains, cb, self.potential, **common)
+            if events is not None:
+                events[1].record()
+        elif fused is not None:
             tr, st = engine.run_transitions(self._kind, self._chains, fused, knobs=self._knobs, events=events, **common)
         else:
             graph = bool(getattr(self._logp_dlogp_func, "cuda_graph", False))

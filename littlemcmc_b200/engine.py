@@ -26,7 +26,7 @@ def padded_ld(ndim):
 
 def as_device_rows(x, n_chains, ndim, device):
     """numpy/torch [D] or [C, D] -> float64 device tensor [C, ld] with zero padding."""
-    t = torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x, dtype=torch.float64, device=device)
+    t = torch.as_tensor(np.array(x, dtype="d") if not torch.is_tensor(x) else x, dtype=torch.float64, device=device)
     if t.ndim == 1:
         t = t.unsqueeze(0).expand(n_chains, -1)
     if t.shape != (n_chains, ndim):
@@ -326,6 +326,99 @@ def run_transitions_callback(kind, chains, callback, *, n_trans, iter0, n_tune, 
     run = CallbackRun(kind, chains, callback, n_trans=n_trans, iter0=iter0, n_tune=n_tune, params=params, seeds=seeds,
                       tapes=tapes, trace=trace, stats=stats, step_size_override=step_size_override)
     run.run(cuda_graph=cuda_graph)
+    return run.trace, run.stats
+
+
+# ---- dense-mass mode ---------------------------------------------------------------------------------------------------
+class DenseRun:
+    """`n_trans` transitions of every chain with a DENSE potential (quadpotential_dense.py), driven by lmc_dense_begin /
+    lmc_dense_advance: after every advance each chain says which batched result it waits for (gradient, velocity,
+    momentum draw, mass-matrix update) and the host computes exactly those, for exactly those chains."""
+
+    def __init__(self, kind, chains, callback, potential, *, n_trans, iter0, n_tune, params, seeds=None, tapes=None,
+                 trace=None, stats=None, stream=None, step_size_override=None):
+        self.lib = L.load()
+        self.kind, self.chains, self.callback, self.potential = kind, chains, callback, potential
+        dev, Cn = chains.device, chains.n_chains
+        ld = chains.ld
+        self.trace, self.stats = _alloc_outputs(chains, n_trans, trace, stats)
+        z = lambda *s: torch.zeros(*s, dtype=torch.float64, device=dev)  # noqa: E731
+        self.q_eval, self.g_eval, self.logp_eval = z(Cn, ld), z(Cn, ld), z(Cn)
+        self.x_eval, self.v_eval = z(Cn, 2, ld), z(Cn, 2, ld)
+        self.n_eval, self.p0_eval = z(Cn, ld), z(Cn, ld)
+        self.need = torch.zeros(Cn, dtype=torch.int32, device=dev)
+        self.need_host = torch.zeros(Cn, dtype=torch.int32).pin_memory()
+        self.n_running = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.c = L.DenseArgs()
+        with torch.cuda.device(dev):
+            self.keep = _fill_base(self.c.base, kind, chains, n_trans=n_trans, iter0=iter0, n_tune=n_tune, params=params,
+                                   seeds=seeds, tapes=tapes, trace=self.trace, stats=self.stats, knobs=None, stream=stream,
+                                   step_size_override=step_size_override)
+            self.c.base.adapt_mass = int(bool(getattr(potential, "_adaptive", False)))
+            nbytes = self.lib.lmc_dense_state_bytes(kind, Cn, chains.ndim, self.c.base.max_treedepth)
+            if nbytes < 0:
+                L.check(int(nbytes), "lmc_dense_state_bytes")
+            self.machine = chains.workspace(nbytes)
+        c = self.c
+        c.q_eval, c.g_eval, c.logp_eval = self.q_eval.data_ptr(), self.g_eval.data_ptr(), self.logp_eval.data_ptr()
+        c.x_eval, c.v_eval = self.x_eval.data_ptr(), self.v_eval.data_ptr()
+        c.n_eval, c.p0_eval, c.need = self.n_eval.data_ptr(), self.p0_eval.data_ptr(), self.need.data_ptr()
+        c.machine, c.machine_bytes, c.n_running = self.machine.data_ptr(), self.machine.numel(), self.n_running.data_ptr()
+        per = (1 << c.base.max_treedepth) + 2 if kind == L.KIND_NUTS else c.base.max_steps + 2
+        self.max_iters = 2 * int(n_trans) * per + 4
+        self.n_grad_evals = self.n_vel_evals = 0
+
+    def _subset(self, mask_host):
+        """-> None when every chain is selected, else an int64 device index tensor."""
+        if mask_host.all():
+            return None
+        return torch.as_tensor(np.nonzero(mask_host)[0], device=self.chains.device)
+
+    def run(self):
+        dev, D = self.chains.device, self.chains.ndim
+        pot = self.potential
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev)
+            self.c.base.stream = stream.cuda_stream
+            L.check(self.lib.lmc_dense_begin(self.kind, C.byref(self.c)), "lmc_dense_begin")
+            LAUNCH_COUNT["kernels"] += 1
+            for _ in range(self.max_iters):
+                self.need_host.copy_(self.need, non_blocking=True)
+                stream.synchronize()                      # the host must know who needs what: one sync per iteration
+                need = self.need_host.numpy()
+                if not need.any():
+                    break
+                m_upd, m_mom = (need & L.NEED_UPDATE) != 0, (need & L.NEED_MOM) != 0
+                m_grad, m_vel = (need & L.NEED_GRAD) != 0, (need & L.NEED_VEL) != 0
+                if m_upd.any():                           # potential.update first: the momentum draw uses the new matrix
+                    pot._update_rows(torch.as_tensor(np.nonzero(m_upd)[0], device=dev), self.chains.q)
+                if m_mom.any():
+                    pot._momentum_rows(self._subset(m_mom), self.n_eval, self.p0_eval)
+                if m_grad.any():
+                    idx = self._subset(m_grad)
+                    qs = self.q_eval[:, :D] if idx is None else self.q_eval[idx][:, :D]
+                    logp, grad = evaluate_callback(self.callback, qs)
+                    if idx is None:
+                        self.g_eval[:, :D] = grad
+                        self.logp_eval.copy_(logp)
+                    else:
+                        self.g_eval[idx, :D] = grad
+                        self.logp_eval[idx] = logp
+                    self.n_grad_evals += 1
+                if m_vel.any():
+                    pot._velocity_rows(self._subset(m_vel), self.x_eval, self.v_eval)
+                    self.n_vel_evals += 1
+                self.c.base.stream = stream.cuda_stream
+                L.check(self.lib.lmc_dense_advance(self.kind, C.byref(self.c)), "lmc_dense_advance")
+                LAUNCH_COUNT["kernels"] += 1
+            else:
+                raise L.LmcError("dense mode: chains still running after %d iterations" % self.max_iters)
+        return self.trace, self.stats
+
+
+def run_transitions_dense(kind, chains, callback, potential, **kw):
+    run = DenseRun(kind, chains, callback, potential, **kw)
+    run.run()
     return run.trace, run.stats
 
 

@@ -7,8 +7,7 @@ methods of the reference API (`velocity`, `energy`, `velocity_energy`, `random`)
 float32 default (quadpotential.py:175-176) only injects rounding noise into the first state of each draw
  and is not reproduced; `dtype` is accepted for signature compatibility.
 
-Dense potentials (QuadPotentialFull / FullInv / FullAdapt) are outside the hot path this package replaces
-(SURVEY.md section 8f, rank 1).
+Dense potentials (QuadPotentialFull / FullInv / FullAdapt) live in quadpotential_dense.py.
 """
 import ctypes as C
 
@@ -39,12 +38,12 @@ def partial_check_positive_definite(C_):
 
 
 def quad_potential(C_, is_cov):
-    """reference quadpotential.py:33-66: build a potential from a scaling vector (matrices: out of scope)."""
+    """reference quadpotential.py:33-66: build a potential from a scaling vector or matrix."""
     C_ = np.asarray(C_)
     partial_check_positive_definite(C_)
     if C_.ndim == 1:
         return QuadPotentialDiag(C_ if is_cov else 1.0 / C_)
-    raise NotImplementedError("dense mass matrices are outside the B200 hot path (SURVEY.md section 8f)")
+    return QuadPotentialFull(C_) if is_cov else QuadPotentialFullInv(C_)
 
 
 class QuadPotential:
@@ -188,13 +187,4 @@ class QuadPotentialDiagAdapt(QuadPotential):
         return self._chains.var[:, : self._n]
 
 
-def _dense(name):
-    def ctor(*a, **k):
-        raise NotImplementedError("%s: dense mass matrices are outside the B200 hot path (SURVEY.md section 8f)" % name)
-    ctor.__name__ = name
-    return ctor
-
-
-QuadPotentialFull = _dense("QuadPotentialFull")
-QuadPotentialFullInv = _dense("QuadPotentialFullInv")
-QuadPotentialFullAdapt = _dense("QuadPotentialFullAdapt")
+from .quadpotential_dense import QuadPotentialFull, QuadPotentialFullAdapt, QuadPotentialFullInv  # noqa: E402,F401

@@ -232,10 +232,16 @@ def init_nuts(logp_dlogp_func, model_ndim, init="auto", random_seed=None, **kwar
         start = np.zeros(model_ndim)
     elif init == "jitter+adapt_diag":
         start = 2 * np.random.rand(model_ndim) - 1                                  # :584
-    elif init in ("adapt_full", "jitter+adapt_full"):
-        raise NotImplementedError("dense mass-matrix adaptation is outside the B200 hot path (SURVEY.md section 8f)")
+    elif init == "adapt_full":
+        start = np.zeros(model_ndim)                                                # :588-592
+    elif init == "jitter+adapt_full":
+        start = 2 * np.random.rand(model_ndim) - 1                                  # :593-597
     else:
         raise ValueError("Unknown initializer: {}.".format(init))
-    potential = QuadPotentialDiagAdapt(model_ndim, start, np.ones(model_ndim), 10)  # :582,587
+    if init.endswith("adapt_full"):
+        from .quadpotential import QuadPotentialFullAdapt
+        potential = QuadPotentialFullAdapt(model_ndim, start, np.eye(model_ndim), 10)
+    else:
+        potential = QuadPotentialDiagAdapt(model_ndim, start, np.ones(model_ndim), 10)  # :582,587
     step = NUTS(logp_dlogp_func=logp_dlogp_func, model_ndim=model_ndim, potential=potential, **kwargs)
     return start, step

@@ -20,17 +20,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
 import littlemcmc as lmc  # noqa: E402  (the reference)
 from oracle.lmc_oracle import dense_gaussian  # noqa: E402  (target density only)
+from tests.dense_utils import spd  # noqa: E402
 
 assert lmc.__file__.startswith("/root/reference"), lmc.__file__
-
-
-def spd(n, seed, cond=30.0):
-    """A well-conditioned random SPD matrix with strong off-diagonal structure."""
-    rs = np.random.RandomState(seed)
-    q, _ = np.linalg.qr(rs.randn(n, n))
-    ev = np.exp(np.linspace(0, np.log(cond), n)) / np.sqrt(cond)
-    m = (q * ev) @ q.T
-    return 0.5 * (m + m.T)
 
 
 def make_potential(case):

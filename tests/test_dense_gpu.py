@@ -1,0 +1,154 @@
+"""Dense-mass mode (QuadPotentialFull / FullInv / FullAdapt, reference
+quadpotential.py:390-615) on the GPU against the CPU oracle, which is pinned to the reference on the dense fixtures
+(tests/test_oracle_golden.py::test_dense_oracle_matches_reference).
+
+Bar (transition-level, as tests/test_gpu_parity.py): integer / boolean statistics and the count of uniforms consumed
+exact; float64 quantities to RTOL = 1e-9.  Licence to differ: summation order of the matrix-vector products
+(BLAS dgemv on the CPU, a warp-per-row reduction / cuBLAS on the GPU), the Cholesky / triangular-solve libraries,
+and velocity(p + dt g) formed as velocity(p) + dt velocity(g).
+"""
+import numpy as np
+import pytest
+
+from tests import dense_utils as du
+from tests import golden_cases as gc
+from tests import parity_utils as pu
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+@pytest.mark.parametrize("name", gc.DENSE_CASE_NAMES)
+def test_dense_transition_level_parity(name):
+    from littlemcmc_b200 import _lib as L
+    case, ref = gc.load(name)
+    ora = du.oracle_run_dense(case)
+    np.testing.assert_allclose(ora["post"]["q"], ref["trace"], rtol=1e-10)          # the oracle side IS the reference
+    q, ad, st, pots, status = du.gpu_run_dense_transitionwise(case, ora)
+    assert (status == 0).all()
+    table = pu.NUTS_STATS if str(case["kind"]) == "nuts" else pu.HMC_STATS
+    assert np.array_equal(st[:, :, L.STAT_N_UNIFORMS], ora["tapes"][2]), "uniform consumption differs"
+    for k, v in ora["stats"].items():
+        g, v = st[:, :, table[k]], np.asarray(v, dtype="d")
+        if k in pu.EXACT:
+            assert np.array_equal(g, v), k
+        else:
+            np.testing.assert_allclose(g, v, rtol=RTOL, atol=1e-12, err_msg=k)
+    np.testing.assert_allclose(q, ora["post"]["q"], rtol=RTOL, atol=1e-12, err_msg="trace")
+    np.testing.assert_allclose(ad, ora["post"]["adapt"], rtol=RTOL, atol=1e-12, err_msg="step-size state")
+    if case["pot"] == "fulladapt":
+        Cn, T = q.shape[:2]
+        for t in range(T):
+            for c in range(Cn):
+                want = ora["post"]["pot"][c][t]
+                for key in ("cov", "chol", "mean_fg", "raw_fg", "mean_bg", "raw_bg", "n_fg", "n_bg"):
+                    np.testing.assert_allclose(pots[t][key][c], want[key], rtol=RTOL, atol=1e-12,
+                                               err_msg="%s (chain %d, transition %d)" % (key, c, t))
+                for key in ("n_samples", "previous_update", "window"):
+                    assert int(pots[t][key][c]) == int(want[key]), (key, c, t)
+
+
+@pytest.mark.parametrize("D,nrhs", [(9, 2), (64, 1), (257, 2), (1000, 2)])
+def test_dense_matvec_kernel(D, nrhs):
+    """lmc_dense_matvec against torch's float64 bmm, with and without a chain index list, odd and even n."""
+    import ctypes as C
+    import torch
+    from littlemcmc_b200 import _lib as L
+    lib = L.load()
+    dev = torch.device("cuda", 0)
+    Cn, lda, ld = 7, D + (D & 1), D + (D & 1)
+    gen = torch.Generator(device=dev).manual_seed(D)
+    A = torch.randn(Cn, D, lda, dtype=torch.float64, device=dev, generator=gen)
+    x = torch.randn(Cn, nrhs, ld, dtype=torch.float64, device=dev, generator=gen)
+    want = torch.einsum("cij,crj->cri", A[:, :, :D], x[:, :, :D])
+    p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
+    for idx in (None, torch.tensor([5, 0, 3], dtype=torch.int32, device=dev)):
+        y = torch.full((Cn, nrhs, ld), float("nan"), dtype=torch.float64, device=dev)
+        n_idx = Cn if idx is None else idx.numel()
+        L.check(lib.lmc_dense_matvec(p(idx), n_idx, p(A), D * lda, lda, D, ld, p(x), p(y), nrhs, None), "matvec")
+        torch.cuda.synchronize()
+        rows = list(range(Cn)) if idx is None else idx.tolist()
+        np.testing.assert_allclose(y[rows][:, :, :D].cpu().numpy(), want[rows].cpu().numpy(), rtol=1e-12, atol=1e-12)
+        others = [c for c in range(Cn) if c not in rows]
+        assert torch.isnan(y[others]).all()                    # unlisted chains are not touched
+    # one matrix shared by all chains (chain_stride 0)
+    y = torch.zeros(Cn, nrhs, ld, dtype=torch.float64, device=dev)
+    L.check(lib.lmc_dense_matvec(None, Cn, p(A[2]), 0, lda, D, ld, p(x), p(y), nrhs, None), "matvec")
+    want0 = torch.einsum("ij,crj->cri", A[2, :, :D], x[:, :, :D])
+    np.testing.assert_allclose(y[:, :, :D].cpu().numpy(), want0.cpu().numpy(), rtol=1e-12, atol=1e-12)
+
+
+def test_dense_cov_update_kernel_matches_weighted_covariance():
+    """lmc_dense_cov_update against the oracle's _WeightedCovariance (reference quadpotential.py:573-621), several
+    samples in a row for a subset of chains."""
+    import torch
+    import littlemcmc_b200 as lmc
+    from littlemcmc_b200 import engine
+    from oracle import lmc_oracle as orc
+    D, Cn = 11, 4
+    rs = np.random.RandomState(3)
+    mean0, cov0 = rs.randn(D), np.eye(D) * 2.0
+    pot = lmc.QuadPotentialFullAdapt(D, mean0, cov0, 5, adaptation_window=4, adaptation_window_multiplier=2)
+    ch = engine.DeviceChains(Cn, D, "cuda:0")
+    pot._bind(ch)
+    refs = [orc.FullAdaptPotential(D, mean0, cov0, 5, adaptation_window=4, adaptation_window_multiplier=2)
+            for _ in range(Cn)]
+    for step in range(14):
+        rows = [c for c in range(Cn) if (step + c) % 3 != 0]         # a different subset of chains every time
+        xs = rs.randn(Cn, D)
+        ch.q[:, :D] = torch.as_tensor(xs, device=ch.device)
+        pot._update_rows(torch.as_tensor(rows, device=ch.device), ch.q)
+        for c in rows:
+            refs[c].update(xs[c], True)
+        for c in range(Cn):
+            np.testing.assert_allclose(pot._cov_all[c, :, :D].cpu().numpy(), refs[c].cov, rtol=1e-12, atol=1e-14)
+            np.testing.assert_allclose(pot._chol_all[c].cpu().numpy(), refs[c].chol, rtol=1e-10, atol=1e-12)
+            assert pot._n_samples_all[c] == refs[c].n_samples and pot._window_all[c] == refs[c].adaptation_window
+            assert pot._previous_update_all[c] == refs[c].previous_update
+            np.testing.assert_allclose(pot._nsamp[c].cpu().numpy(), [refs[c].fg.n_samples, refs[c].bg.n_samples])
+
+
+def test_equal_dense_and_random_dense():
+    """reference tests/test_quadpotential.py:67-87 (dense / inverse forms agree) and :104-122 (random() covariance)."""
+    import littlemcmc_b200 as lmc
+    np.random.seed(42)
+    for _ in range(3):
+        cov = np.random.rand(5, 5)
+        cov += cov.T
+        cov += 10 * np.eye(5)
+        inv = np.linalg.inv(cov)
+        x = np.random.randn(5)
+        pots = [lmc.quad_potential(cov, False), lmc.quad_potential(inv, True)]
+        assert isinstance(pots[0], lmc.QuadPotentialFullInv) and isinstance(pots[1], lmc.QuadPotentialFull)
+        v = np.linalg.solve(cov, x)
+        e = 0.5 * x.dot(v)
+        for pot in pots:
+            np.testing.assert_allclose(pot.velocity(x), v, rtol=1e-10)
+            np.testing.assert_allclose(pot.energy(x), e, rtol=1e-10)
+            v_out = np.empty(5)
+            np.testing.assert_allclose(pot.velocity_energy(x, v_out), e, rtol=1e-10)
+            np.testing.assert_allclose(v_out, v, rtol=1e-10)
+        for pot in (lmc.QuadPotentialFull(cov), lmc.QuadPotentialFullInv(inv)):
+            cov_ = np.cov(np.array([pot.random() for _ in range(1000)]).T)
+            assert np.allclose(cov_, inv, atol=0.1)
+
+
+def test_init_nuts_adapt_full_and_sampling_recovers_covariance():
+    """reference sampling.py:588-597 (init='adapt_full' / 'jitter+adapt_full') and an end-to-end run: 64 chains with a
+    per-chain adapted dense mass matrix recover a strongly correlated Gaussian."""
+    import torch
+    import littlemcmc_b200 as lmc
+    D = 6
+    prec = du.spd(D, 5, cond=50.0)
+    cov = np.linalg.inv(prec)
+    target = du.torch_dense_gaussian(prec, torch.device("cuda", 0))
+    for init in ("adapt_full", "jitter+adapt_full"):
+        start, step = lmc.init_nuts(logp_dlogp_func=target, model_ndim=D, init=init, random_seed=3)
+        assert isinstance(start, np.ndarray) and start.shape == (D,)
+        assert isinstance(step, lmc.NUTS) and isinstance(step.potential, lmc.QuadPotentialFullAdapt)
+    trace, stats = lmc.sample(target, D, draws=150, tune=250, init="adapt_full", chains=64, random_seed=11)
+    assert trace.shape == (64, 150, D) and stats["depth"].shape == (64, 150, 1)
+    flat = trace.reshape(-1, D)
+    np.testing.assert_allclose(np.cov(flat.T), cov, atol=0.12 * np.abs(cov).max())
+    assert stats["diverging"].sum() == 0
