@@ -140,8 +140,19 @@ __device__ __forceinline__ double philox_uniform(uint64_t seed, int64_t it, uint
                                 (uint32_t)seed, (uint32_t)(seed >> 32));
   return u52(r.x, r.y);
 }
+// Code that runs once per transition (not once per leapfrog) is kept OUT OF LINE: the sampler kernel's hot loop has to
+// share a 32 KB L1.5 instruction cache with it (profiles/r01d_ncu_full.md: 18% of warp samples wait for instructions),
+// and an inlined double-precision log / sincospi / pow per register pair is several KB each.
+#ifdef LMC_INLINE_COLD
+#define LMC_COLD __device__ __forceinline__
+#else
+#define LMC_COLD static __device__ __noinline__
+#endif
+// IEEE 1/sqrt(x) and a/b (two correctly rounded operations each, as NumPy computes them): ~45 instructions apiece
+LMC_COLD double inv_sqrt_cold(double x) { return 1.0 / sqrt(x); }
+LMC_COLD double div_cold(double a, double b) { return a / b; }
 // standard normals for elements (2j, 2j+1) of the momentum draw of transition `it` (Box-Muller)
-__device__ __forceinline__ double2 philox_normal_pair(uint64_t seed, int64_t it, uint32_t j) {
+LMC_COLD double2 philox_normal_pair(uint64_t seed, int64_t it, uint32_t j) {
   const u32x4 r = philox4x32_10(u32x4{j, (uint32_t)it, (uint32_t)((uint64_t)it >> 32), kTagNormal},
                                 (uint32_t)seed, (uint32_t)(seed >> 32));
   const double rad = sqrt(-2.0 * log(u52(r.x, r.y)));

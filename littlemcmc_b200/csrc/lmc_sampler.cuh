@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
         status |= LMC_STATUS_BAD_INITIAL_ENERGY;
         dead = true;
       } else {
-        double eps = exp(adapt_step ? da.log_step : da.log_bar);  // step_sizes.py:58-69
+        double eps = exp_cold(adapt_step ? da.log_step : da.log_bar);  // step_sizes.py:58-69
         if (a.step_size_override) eps = __ldg(a.step_size_override + chain);  // step_rand hook, base_hmc.py:154-155
 
         double accept_stat, stat_a, stat_b, stat_energy, stat_energy_error, stat_c, stat_logp;
@@ -369,8 +369,8 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
           srow[LMC_STAT_MODEL_LOGP] = stat_logp;
           srow[LMC_STAT_DIVERGING] = diverging ? 1.0 : 0.0;
           srow[LMC_STAT_TUNE] = tune ? 1.0 : 0.0;
-          srow[LMC_STAT_STEP_SIZE] = exp(da.log_step);
-          srow[LMC_STAT_STEP_SIZE_BAR] = exp(da.log_bar);
+          srow[LMC_STAT_STEP_SIZE] = exp_cold(da.log_step);
+          srow[LMC_STAT_STEP_SIZE_BAR] = exp_cold(da.log_bar);
           srow[LMC_STAT_N_UNIFORMS] = (double)uc;
           srow[LMC_STAT_REACHED_MAX_TREEDEPTH] = reached_max ? 1.0 : 0.0;
         }

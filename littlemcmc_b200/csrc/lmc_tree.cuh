@@ -371,15 +371,21 @@ struct DualAvg {
   double log_step, log_bar, hbar, count, mu;
 };
 // DualAverageAdaptation.update (step_sizes.py:71-92)
-__device__ __forceinline__ void dual_average_update(DualAvg& s, double accept_stat, double target, double gamma,
-                                                    double k, double t0) {
+LMC_COLD DualAvg dual_average_step(DualAvg s, double accept_stat, double target, double gamma, double k, double t0) {
   const double w = 1.0 / (s.count + t0);
   s.hbar = (1.0 - w) * s.hbar + w * (target - accept_stat);
   s.log_step = s.mu - s.hbar * sqrt(s.count) / gamma;
   const double mk = pow(s.count, -k);
   s.log_bar = mk * s.log_step + (1.0 - mk) * s.log_bar;
   s.count += 1.0;
+  return s;
 }
+__device__ __forceinline__ void dual_average_update(DualAvg& s, double accept_stat, double target, double gamma,
+                                                    double k, double t0) {
+  s = dual_average_step(s, accept_stat, target, gamma, k, t0);
+}
+// exp() for once-per-transition statistics
+LMC_COLD double exp_cold(double x) { return exp(x); }
 
 struct WelfordScalars {
   double w_fg, w_bg;
@@ -414,7 +420,7 @@ __device__ __forceinline__ void welford_update(int lane, int D, int ldh, double*
       m2 = axpy2(m2, prop_bg, od);
       nd = make_double2(add_rn(q[k].x, -m2.x), add_rn(q[k].y, -m2.y));
       r2 = add2(r2, mul2(od, nd));
-      var[k] = make_double2(r.x / ws.w_fg, r.y / ws.w_fg);  // _update_from_weightvar(foreground) (:226-229)
+      var[k] = make_double2(div_cold(r.x, ws.w_fg), div_cold(r.y, ws.w_fg));  // _update_from_weightvar(fg) (:226-229)
       if (2 * j >= D) var[k].x = 0.0;
       if (2 * j + 1 >= D) var[k].y = 0.0;
       if (sw) {  // foreground <- background, background <- fresh (:240-243)
@@ -453,8 +459,8 @@ __device__ __forceinline__ void draw_momentum(int lane, int D, const double* nor
     } else if (2 * j < D) {
       n = philox_normal_pair(seed, it, (uint32_t)j);
     }
-    p[k].x = (2 * j < D) ? mul_rn(1.0 / sqrt(var[k].x), n.x) : 0.0;
-    p[k].y = (2 * j + 1 < D) ? mul_rn(1.0 / sqrt(var[k].y), n.y) : 0.0;
+    p[k].x = (2 * j < D) ? mul_rn(inv_sqrt_cold(var[k].x), n.x) : 0.0;
+    p[k].y = (2 * j + 1 < D) ? mul_rn(inv_sqrt_cold(var[k].y), n.y) : 0.0;
   }
 }
 

@@ -70,15 +70,15 @@ def test_nuts_tuning():
 
 
 def test_init_nuts():
-    """reference tests/test_sampling.py:21-34 (diagonal initialisers)."""
+    """reference tests/test_sampling.py:21-34: all four initialisers."""
     lmc = _lmc()
     target = lmc.targets.StdNormal(1)
-    for init in ("auto", "adapt_diag", "jitter+adapt_diag"):
+    for init in ("auto", "adapt_diag", "jitter+adapt_diag", "adapt_full", "jitter+adapt_full"):
         start, step = lmc.init_nuts(logp_dlogp_func=target, model_ndim=1, init=init)
         assert isinstance(start, np.ndarray) and len(start) == 1
         assert isinstance(step, lmc.NUTS)
-    with pytest.raises(NotImplementedError):
-        lmc.init_nuts(logp_dlogp_func=target, model_ndim=1, init="adapt_full")
+    with pytest.raises(ValueError):
+        lmc.init_nuts(logp_dlogp_func=target, model_ndim=1, init="no such initialiser")
 
 
 @pytest.mark.parametrize("method", ["HamiltonianMC", "NUTS"])
