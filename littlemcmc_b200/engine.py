@@ -174,6 +174,8 @@ def run_transitions(kind, chains, target, *, n_trans, iter0, n_tune, params, see
     dev = chains.device
     Cn, D = chains.n_chains, chains.ndim
     trace, stats = _alloc_outputs(chains, n_trans, trace, stats)
+    if n_trans == 0 or Cn == 0:      # nothing to do (empty tensors have no device pointer to hand to the library)
+        return trace, stats
     a = L.SamplerArgs()
     with torch.cuda.device(dev):
         keep = _fill_base(a, kind, chains, n_trans=n_trans, iter0=iter0, n_tune=n_tune, params=params, seeds=seeds,

@@ -115,3 +115,29 @@ def test_no_cpu_fallback():
     from littlemcmc_b200 import _lib as L, engine
     with pytest.raises(L.LmcError):
         engine.DeviceChains(2, 3, "cpu")
+
+
+def test_dense_potential_validation_and_factory():
+    """reference quadpotential.py:33-66 (quad_potential dispatch), :484-499 (QuadPotentialFullAdapt argument checks);
+    host-side only: no device is touched until a step method binds the potential."""
+    import littlemcmc_b200 as lmc
+    from littlemcmc_b200.quadpotential import PositiveDefiniteError
+    cov = np.array([[2.0, 0.3], [0.3, 1.0]])
+    assert isinstance(lmc.quad_potential(cov, True), lmc.QuadPotentialFull)
+    assert isinstance(lmc.quad_potential(cov, False), lmc.QuadPotentialFullInv)
+    assert isinstance(lmc.quad_potential(np.array([1.0, 2.0]), True), lmc.QuadPotentialDiag)
+    with pytest.raises(PositiveDefiniteError):
+        lmc.quad_potential(np.array([[1.0, 0.0], [0.0, -1.0]]), True)
+    with pytest.raises(ValueError, match="two-dimensional"):
+        lmc.QuadPotentialFullAdapt(2, np.zeros(2), np.ones(2), 1)
+    with pytest.raises(ValueError, match="one-dimensional"):
+        lmc.QuadPotentialFullAdapt(2, np.zeros((2, 1)), np.eye(2), 1)
+    with pytest.raises(ValueError, match="Wrong shape for initial_cov"):
+        lmc.QuadPotentialFullAdapt(3, np.zeros(3), np.eye(2), 1)
+    with pytest.raises(ValueError, match="Wrong shape for initial_mean"):
+        lmc.QuadPotentialFullAdapt(2, np.zeros(3), np.eye(2), 1)
+    pot = lmc.QuadPotentialFullAdapt(2, np.zeros(2))              # initial_cov None -> identity with weight 1 (:500-502)
+    assert pot._initial_weight == 1 and np.array_equal(pot._initial_cov, np.eye(2))
+    for init in ("adapt_full", "jitter+adapt_full"):
+        start, step = lmc.init_nuts(lmc.targets.StdNormal(3), 3, init=init, random_seed=4)
+        assert isinstance(step.potential, lmc.QuadPotentialFullAdapt) and start.shape == (3,)
