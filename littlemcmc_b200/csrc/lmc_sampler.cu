@@ -42,6 +42,18 @@ int run_gauss_nuts(const lmc_sampler_args& a, const DiagGaussian& t);
 int run_gauss_hmc(const lmc_sampler_args& a, const DiagGaussian& t);
 int run_funnel_nuts(const lmc_sampler_args& a, const Funnel& t);
 int run_funnel_hmc(const lmc_sampler_args& a, const Funnel& t);
+// lean NUTS kernel (lmc_sampler_lean.cuh): forced with tune_group < 0 (threads per chain = -tune_group); the default
+// for 513..1024 dimensions, where 128 threads x 4 pairs with three vectors in registers fit four chains per SM
+// instead of three (measured +8% at 1024 chains x 1000 dimensions)
+int run_gauss_nuts_lean(const lmc_sampler_args& a, const DiagGaussian& t, int group);
+int run_funnel_nuts_lean(const lmc_sampler_args& a, const Funnel& t, int group);
+bool pick_lean_shape(int ndim, int group, int* G, int* NP);
+static int lean_group(const lmc_sampler_args* a, int kind) {
+  if (kind != KIND_NUTS) return 0;
+  if (a->tune_group < 0) return -a->tune_group;
+  const int pairs = (a->ndim + 1) / 2;
+  return (a->tune_group == 0 && pairs > 256 && pairs <= 512) ? 128 : 0;
+}
 
 static int sample_entry(const lmc_sampler_args* a, int kind) {
   const int rc = check_args(a, kind);
@@ -49,9 +61,11 @@ static int sample_entry(const lmc_sampler_args* a, int kind) {
   if (a->n_chains == 0 || a->n_trans == 0) return LMC_OK;
   if (a->target.kind == LMC_TARGET_DIAG_GAUSSIAN) {
     DiagGaussian t{reinterpret_cast<const double2*>(a->target.tau)};
+    if (lean_group(a, kind)) return run_gauss_nuts_lean(*a, t, lean_group(a, kind));
     return kind == KIND_NUTS ? run_gauss_nuts(*a, t) : run_gauss_hmc(*a, t);
   }
   Funnel t{1.0 / (a->target.v_scale * a->target.v_scale), 0.5 * (double)(a->ndim - 1)};
+  if (lean_group(a, kind)) return run_funnel_nuts_lean(*a, t, lean_group(a, kind));
   return kind == KIND_NUTS ? run_funnel_nuts(*a, t) : run_funnel_hmc(*a, t);
 }
 
@@ -63,7 +77,11 @@ extern "C" int64_t lmc_workspace_bytes(int32_t kind, int32_t n_chains, int32_t n
   if (kind == lmc::KIND_HMC) return (int64_t)lmc::sched_bytes(n_chains);
   if (kind != lmc::KIND_NUTS || max_treedepth < 1 || max_treedepth > lmc::kMaxDepth) return LMC_ERR_UNSUPPORTED;
   lmc::Shape s;
-  if (!lmc::pick_shape(ndim, tune_group, &s)) return LMC_ERR_UNSUPPORTED;
+  if (tune_group < 0) {
+    if (!lmc::pick_lean_shape(ndim, -tune_group, &s.G, &s.NP)) return LMC_ERR_UNSUPPORTED;
+  } else if (!lmc::pick_shape(ndim, tune_group, &s)) {
+    return LMC_ERR_UNSUPPORTED;
+  }
   // resident groups are bounded by 2048 threads per SM and by the number of chains
   int dev = 0, n_sm = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);

@@ -104,3 +104,24 @@ def test_step_rand_hook(callback):
     pu.assert_parity(res, rtol=RTOL)
     plain = pu.run_case_on_gpu_and_oracle("nuts_diag_d37", n_trans=30, callback=callback)
     assert not np.array_equal(res.gpu_trace, plain.gpu_trace)
+
+
+@pytest.mark.parametrize("group", [-64, -128])
+@pytest.mark.parametrize("name", ["nuts_illcond_d1000", "nuts_diag_d37", "nuts_static_d100", "nuts_funnel_d10", "nuts_b1_d10"])
+def test_lean_kernel_parity(name, group):
+    """The lean NUTS kernel (lmc_sampler_lean.cuh: only q, p, grad in registers; selected with a negative group knob)
+    against the oracle, transition level, with its scratch in shared memory and all-global."""
+    for smem in (-1, 0):
+        res = pu.run_case_on_gpu_and_oracle(name, knobs=dict(group=group, smem_vecs=smem))
+        pu.assert_parity(res, rtol=RTOL)
+
+
+@pytest.mark.parametrize("name", ["nuts_diag_d37", "nuts_funnel_d10"])
+def test_lean_kernel_equals_default_kernel_on_chained_runs(name):
+    """Same group width => same reduction tree => bit-identical chained runs (adaptation included)."""
+    a = pu.run_case_on_gpu_and_oracle(name, n_trans=80, chained=True, knobs=dict(group=64))
+    b = pu.run_case_on_gpu_and_oracle(name, n_trans=80, chained=True, knobs=dict(group=-64))
+    assert np.array_equal(a.gpu_trace, b.gpu_trace)
+    for k in a.gpu_stats:
+        assert np.array_equal(a.gpu_stats[k], b.gpu_stats[k], equal_nan=True), k
+    assert np.array_equal(a.gpu_var, b.gpu_var) and np.array_equal(a.gpu_adapt, b.gpu_adapt)

@@ -9,6 +9,6 @@ timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; ech
 cat gpurun_out/bench.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv \
   python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/bench_under_ncu.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:sampler_kernel -s 1 -c 1 -f -o gpurun_out/prof_sampler \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:sampler_ -s 1 -c 1 -f -o gpurun_out/prof_sampler \
   python tools/quick_bench.py 1024 1000 4 > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log
