@@ -4,13 +4,16 @@
 namespace lmc {
 
 // (threads per chain, pairs per thread, min resident CTAs per SM)
-#define LMC_LEAN_SHAPES(X) X(64, 8, 5) X(64, 4, 8) X(128, 4, 4) X(128, 2, 6)
+#ifndef LMC_LEAN_MC_128_4
+#define LMC_LEAN_MC_128_4 4
+#endif
+#define LMC_LEAN_SHAPES(X) X(64, 8, 5) X(64, 4, 8) X(128, 4, LMC_LEAN_MC_128_4) X(128, 2, 6) X(256, 2, 3)
 
 bool pick_lean_shape(int ndim, int group, int* G, int* NP) {
   const int pairs = (ndim + 1) / 2;
 #define LMC_X(g, np, mc) \
   if (group == g && g * np >= pairs) { *G = g; *NP = np; return true; }
-  LMC_X(64, 4, 8) LMC_X(64, 8, 5) LMC_X(128, 2, 6) LMC_X(128, 4, 4)
+  LMC_X(64, 4, 8) LMC_X(64, 8, 5) LMC_X(128, 2, 6) LMC_X(128, 4, 4) LMC_X(256, 2, 3)
 #undef LMC_X
   return false;
 }

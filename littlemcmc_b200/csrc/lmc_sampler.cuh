@@ -356,8 +356,9 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
 #pragma unroll
         for (int k = 0; k < NP; ++k) {
           const int j = lane + k * G;
-          if (2 * j < D) trow[2 * j] = q[k].x;
-          if (2 * j + 1 < D) trow[2 * j + 1] = q[k].y;
+          // the trace is write-once streaming output: evict-first, so it does not push the tree scratch out of L2
+          if (2 * j < D) __stcs(trow + 2 * j, q[k].x);
+          if (2 * j + 1 < D) __stcs(trow + 2 * j + 1, q[k].y);
         }
         if (lane == 0) {
           srow[LMC_STAT_DEPTH] = stat_a;

@@ -3,11 +3,12 @@
 // being assembled live in shared memory, and the subtree's left-edge momentum is never copied at all: it is referenced
 // by the id of the stack vector that already holds it.
 //
-// Why.  The per-leaf critical path of the sampler is scalar (two group reductions, one exp, tree-weight bookkeeping):
-// ~6000 cycles per leaf for a lone chain regardless of how many warps share its vectors (profiles/), so
-// throughput ~ resident chains per SM.  sampler_kernel keeps six vectors in registers (q, p, g, var, cur_lp, cur_ps):
-// at D = 1000 that is 168 registers x 128 threads per chain and three chains per SM.  Three vectors in registers let a
-// chain be owned by 64 threads x 8 pairs: half the redundant scalar work per chain and five chains per SM.
+// Why.  sampler_kernel keeps six vectors in registers (q, p, g, var, cur_lp, cur_ps): at D = 1000 that is 168 registers
+// x 128 threads per chain and three chains per SM, and its throughput still grows with the number of resident chains
+// (1 / 2 / 3 chains per SM: 4.9 / 8.3 / 9.9 x 10^7 leapfrog/s).  With three vectors in registers the same 128 threads
+// x 4 pairs need 128 registers: four chains per SM, +8% (1.07 x 10^8 in the same probe).  Measured and rejected on the
+// way: 64 threads x 8 pairs (six chains per SM but twice the vector instructions per warp: 7.8 x 10^7), 256 x 2
+// (8.0 x 10^7), five chains per SM at 96 registers (spills: 8.0 x 10^7).
 //
 // Everything observable is identical to sampler_kernel: same arithmetic per element, same reduction tree per group
 // shape, same uniforms in the same order; tests/test_gpu_parity.py runs both against the oracle.
@@ -404,8 +405,9 @@ __global__ void __launch_bounds__(G, MINCTAS) sampler_lean_kernel(const lmc_samp
 #pragma unroll
         for (int k = 0; k < NP; ++k) {
           const int j = lane + k * G;
-          if (2 * j < D) trow[2 * j] = q[k].x;
-          if (2 * j + 1 < D) trow[2 * j + 1] = q[k].y;
+          // the trace is write-once streaming output: evict-first, so it does not push the tree scratch out of L2
+          if (2 * j < D) __stcs(trow + 2 * j, q[k].x);
+          if (2 * j + 1 < D) __stcs(trow + 2 * j + 1, q[k].y);
         }
         if (lane == 0) {
           srow[LMC_STAT_DEPTH] = (double)tr.depth;
