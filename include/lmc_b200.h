@@ -311,6 +311,15 @@ int lmc_rng_fill(const uint64_t* seeds, int32_t n_chains, int32_t ndim, int64_t 
 int lmc_memcpy2d_d2h(void* dst_host, int64_t dpitch, const void* src_device, int64_t spitch, int64_t width_bytes,
                      int64_t height, void* stream);
 
+/* Per-chain moments of the draws, the reduction behind cross-chain diagnostics (the reference has
+ * only the per-run warnings of base_hmc.py:202-230 and leaves convergence checks to the caller).  One pass over
+ * trace[chain * chain_stride + t * draw_stride + i]: the n_draws draws of every chain are cut into n_seg contiguous
+ * segments (the last one takes the remainder) and for each (chain, segment, i) the kernel writes the segment's mean
+ * and centred sum of squares M2 = sum (x - mean)^2.  mean, m2: [n_chains, n_seg, ndim].  n_seg = 2 gives the half
+ * chains of split R-hat.  HBM-bound: 8 bytes per draw element, read once. */
+int lmc_chain_moments(const double* trace, int32_t n_chains, int32_t n_draws, int32_t ndim, int64_t chain_stride,
+                      int64_t draw_stride, int32_t n_seg, double* mean, double* m2, void* stream);
+
 /* Last CUDA error string seen by the library on this thread (host pointer, static storage). */
 const char* lmc_last_error(void);
 

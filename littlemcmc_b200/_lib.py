@@ -81,6 +81,7 @@ SYMBOLS = {
     "lmc_dense_advance": (C.c_int, [_I32, C.POINTER(DenseArgs)]),
     "lmc_dense_matvec": (C.c_int, [_P, _I32, _P, _I64, _I64, _I32, _I64, _P, _P, _I32, _P]),
     "lmc_dense_cov_update": (C.c_int, [_P, _I32, _I32, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "lmc_chain_moments": (C.c_int, [_P, _I32, _I32, _I32, _I64, _I64, _I32, _P, _P, _P]),
     "lmc_compute_state": (C.c_int, [C.POINTER(Target), _I32, _I32, _I64, _P, _P, _P, _I64, _P, _P, _P, _P, _P]),
     "lmc_leapfrog_step": (C.c_int, [C.POINTER(Target), _I32, _I32, _I64, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P,
                                     _P, _P, _P]),
