@@ -78,9 +78,62 @@ class GpuLeapfrogIntegrator:
         g[:, :D] = grad
         return logp.contiguous(), g
 
+    # -- dense potentials: velocity is a matrix product (quadpotential_dense.py), the rest is elementwise ---------------
+    def _dense_velocity(self, rows, D):
+        """rows: [C, ld] -> velocity of every row, [C, ld].  Shared-matrix potentials serve any number of rows; a
+        per-chain adapted potential serves its bound chains row by row, or a single vector with the last chain's matrix."""
+        pot = self._potential
+        dev = rows.device
+        if getattr(pot, "_dev", None) != dev:
+            pot._to_device(dev, pot._chains.n_chains if pot._chains is not None else 1)
+        Cn, ld = rows.shape
+        per_chain = getattr(pot, "_nc", None)
+        if per_chain is not None and Cn != per_chain:
+            out = torch.zeros_like(rows)
+            for c in range(Cn):
+                out[c, :D] = pot._velocity_one(rows[c, :D].contiguous())
+            return out
+        x = torch.zeros(Cn, 2, ld, dtype=torch.float64, device=dev)
+        x[:, 0] = rows
+        v = torch.zeros_like(x)
+        pot._velocity_rows(None, x, v)
+        return v[:, 0].contiguous()
+
+    def _dense_compute_state(self, q, p):
+        qr, one_d, was_np = self._rows(q)
+        pr, _, _ = self._rows(p)
+        D = (np.asarray(q).shape if was_np else q.shape)[-1]
+        logp, g = self._callback(qr, D)
+        v = self._dense_velocity(pr, D)
+        energy = 0.5 * (pr * v).sum(1) - logp                                       # integration.py:63-65
+        o = lambda t: self._out(t, D, one_d, was_np)  # noqa: E731
+        sc = lambda t: (t[0].item() if one_d else (t.cpu().numpy() if was_np else t))  # noqa: E731
+        return State(q, p, o(v), o(g), sc(energy), sc(logp))
+
+    def _dense_step(self, epsilon, state):
+        qr, one_d, was_np = self._rows(state.q)
+        pr, _, _ = self._rows(state.p)
+        gr, _, _ = self._rows(state.q_grad)
+        Cn = qr.shape[0]
+        D = (np.asarray(state.q).shape if was_np else state.q.shape)[-1]
+        eps = torch.as_tensor(np.broadcast_to(np.asarray(epsilon, dtype="d"), (Cn,)).copy(), device=qr.device) \
+            if not torch.is_tensor(epsilon) else epsilon.to(torch.float64).expand(Cn).contiguous()
+        dt = (0.5 * eps)[:, None]
+        p_half = pr + dt * gr                                                       # integration.py:108
+        q_new = qr + eps[:, None] * self._dense_velocity(p_half, D)                 # :111-112
+        logp, g_new = self._callback(q_new, D)                                      # :115
+        p_new = p_half + dt * g_new                                                 # :116
+        v_new = self._dense_velocity(p_new, D)                                      # :118
+        energy = 0.5 * (p_new * v_new).sum(1) - logp                                # :119-120
+        o = lambda t: self._out(t, D, one_d, was_np)  # noqa: E731
+        sc = lambda t: (t[0].item() if one_d else (t.cpu().numpy() if was_np else t))  # noqa: E731
+        return State(o(q_new), o(p_new), o(v_new), o(g_new), sc(energy), sc(logp))
+
     # -- the reference API -------------------------------------------------------------------------------------------
     def compute_state(self, q, p):
         """reference integration.py:52-66."""
+        if getattr(self._potential, "_dense", False):
+            return self._dense_compute_state(q, p)
         lib = L.load()
         qr, one_d, was_np = self._rows(q)
         pr, _, _ = self._rows(p)
@@ -109,6 +162,8 @@ class GpuLeapfrogIntegrator:
 
     def step(self, epsilon, state, out=None):
         """reference integration.py:68-121 (epsilon may be negative; scalar or one value per chain)."""
+        if getattr(self._potential, "_dense", False):
+            return self._dense_step(epsilon, state)
         lib = L.load()
         qr, one_d, was_np = self._rows(state.q)
         pr, _, _ = self._rows(state.p)

@@ -152,3 +152,37 @@ def test_init_nuts_adapt_full_and_sampling_recovers_covariance():
     flat = trace.reshape(-1, D)
     np.testing.assert_allclose(np.cov(flat.T), cov, atol=0.12 * np.abs(cov).max())
     assert stats["diverging"].sum() == 0
+
+
+def test_dense_integrator_matches_oracle_and_is_reversible():
+    """`step.integrator.compute_state / step` (reference integration.py:52-121) with dense potentials: one leapfrog
+    against the oracle, and the reference's reversibility test (tests/test_hmc.py:23-40) with a dense matrix."""
+    import littlemcmc_b200 as lmc
+    from oracle import lmc_oracle as orc
+    D = 12
+    prec = du.spd(D, 7)
+    cov = np.linalg.inv(du.spd(D, 8))
+    f = orc.dense_gaussian(prec)
+    rs = np.random.RandomState(0)
+    for pot, opot in ((lmc.QuadPotentialFull(cov), orc.FullPotential(cov)),
+                      (lmc.QuadPotentialFullInv(np.linalg.inv(cov)), orc.FullInvPotential(np.linalg.inv(cov)))):
+        step = lmc.HamiltonianMC(logp_dlogp_func=f, model_ndim=D, potential=pot)
+        q0, p0 = rs.randn(D), rs.randn(D)
+        start = step.integrator.compute_state(q0, p0)
+        ostart = orc.compute_state(f, opot, q0, p0)
+        np.testing.assert_allclose(start.v, ostart.v, rtol=1e-11)
+        np.testing.assert_allclose(start.energy, ostart.energy, rtol=1e-11)
+        for eps in (0.1, -0.07):
+            got, want = step.integrator.step(eps, start), orc.leapfrog(f, opot, eps, ostart)
+            for name in ("q", "p", "v", "q_grad"):
+                np.testing.assert_allclose(getattr(got, name), getattr(want, name), rtol=1e-10, atol=1e-12, err_msg=name)
+            np.testing.assert_allclose(got.energy, want.energy, rtol=1e-10)
+        for epsilon in (0.01, 0.1):
+            for n_steps in (1, 2, 3, 4, 20):
+                state = start
+                for _ in range(n_steps):
+                    state = step.integrator.step(epsilon, state)
+                for _ in range(n_steps):
+                    state = step.integrator.step(-epsilon, state)
+                np.testing.assert_allclose(state.q, start.q, rtol=1e-5)
+                np.testing.assert_allclose(state.p, start.p, rtol=1e-5)
