@@ -41,23 +41,29 @@ WORKLOADS = {
 }
 
 
-def make_target_np(kind, D):
-    """The oracle-side callable and the parameters of the fused target."""
-    from oracle import lmc_oracle as orc
+def target_params(kind, D):
+    """Parameters of the synthetic target densities."""
     if kind == "gauss":
         sigma = 10 ** np.linspace(-0.5, 0.5, D)
-        return orc.diag_gaussian(1 / sigma**2), dict(tau=1 / sigma**2)
+        return dict(tau=1 / sigma**2)
     if kind == "illcond":
-        sig2 = 10 ** np.linspace(0, 4, D)
-        return orc.diag_gaussian(1 / sig2), dict(tau=1 / sig2)
-    return orc.neal_funnel(D), dict()
+        return dict(tau=1 / 10 ** np.linspace(0, 4, D))
+    return dict()
+
+
+def make_target_np(kind, D):
+    """CPU arm only: the oracle's NumPy callable for the same density (the GPU arm never imports oracle/)."""
+    from oracle import lmc_oracle as orc
+    if kind in ("gauss", "illcond"):
+        return orc.diag_gaussian(target_params(kind, D)["tau"])
+    return orc.neal_funnel(D)
 
 
 # ---- CPU arm: the oracle port of the reference on the host cores -------------------------------------------------------
 def _cpu_worker(args):
     kind, D, max_depth, n_trans, n_tune, seed = args
     from oracle import lmc_oracle as orc
-    f, _ = make_target_np(kind, D)
+    f = make_target_np(kind, D)
     smp = orc.Sampler(f, D, orc.DiagPotential(D, var=np.ones(D), initial_mean=np.zeros(D), initial_weight=10.0),
                       kind="nuts", max_treedepth=max_depth)
     rng = np.random.RandomState(seed)
@@ -173,7 +179,7 @@ def run_gpu_arm(args, wl):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    _, tparams = make_target_np(kind, D)
+    tparams = target_params(kind, D)
     target = (lmc.targets.NealFunnel(D) if kind == "funnel" else lmc.targets.DiagGaussian(tau=tparams["tau"]))
     if args.logp != "fused":   # the density as a batched torch op between launches (callback mode)
         target = target.torch_batched(dev, cuda_graph=(args.logp == "torch-graph"))
