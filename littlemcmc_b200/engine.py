@@ -12,6 +12,9 @@ import torch
 from . import _lib as L
 
 
+import os as _os
+_DIRECT_CB = _os.environ.get("LMC_DIRECT_CB", "1") == "1"     # experiment switch (callback output buffers, see CallbackRun)
+
 # launches of this library's kernels enqueued by this process (bench.py reports the count inside its timed region)
 LAUNCH_COUNT = {"kernels": 0}
 
@@ -271,13 +274,13 @@ class CallbackRun:
         c = self.c
         # hand the callback's own output buffers to the kernel when their layout allows it (rows of D = ld doubles,
         # 16-byte aligned): saves two copy kernels per gradient evaluation in this launch-latency-bound mode
-        if (D == self.chains.ld and grad.is_contiguous() and grad.dtype == torch.float64 and grad.data_ptr() % 16 == 0
+        if (_DIRECT_CB and D == self.chains.ld and grad.is_contiguous() and grad.dtype == torch.float64 and grad.data_ptr() % 16 == 0
                 and grad.device == self.q_eval.device):
             c.g_eval = grad.data_ptr()
         else:
             self.g_eval[:, :D].copy_(grad)
             c.g_eval = self.g_eval.data_ptr()
-        if logp.is_contiguous() and logp.dtype == torch.float64 and logp.device == self.q_eval.device:
+        if _DIRECT_CB and logp.is_contiguous() and logp.dtype == torch.float64 and logp.device == self.q_eval.device:
             c.logp_eval = logp.data_ptr()
         else:
             self.logp_eval.copy_(logp)
