@@ -156,8 +156,11 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
     bool dead = ((unsigned)chain & kDeadBit) != 0u;
     chain &= 0x7fffffff;
     const size_t row = (size_t)chain * a.n_trans + t;
-    double* const srow = a.stats + row * LMC_NSTATS;
-    double* const trow = a.trace + (size_t)chain * a.trace_chain_stride + (size_t)t * a.trace_draw_stride;
+    // output rows of this unit: computed where they are written (epilogue / dead-chain fill), not held across the tree
+    auto stats_row = [&]() -> double* { return a.stats + row * LMC_NSTATS; };
+    auto trace_row = [&]() -> double* {
+      return a.trace + (size_t)chain * a.trace_chain_stride + (size_t)t * a.trace_draw_stride;
+    };
     int status = 0;
 
     if (!dead) {
@@ -168,11 +171,8 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
       mask_tail<G, NP>(lane, D, q);
       mask_tail<G, NP>(lane, D, var);
 
-      double* const ad = a.adapt + (size_t)chain * LMC_ADAPT_STRIDE;
-      DualAvg da{__ldcg(ad + LMC_ADAPT_LOG_STEP), __ldcg(ad + LMC_ADAPT_LOG_BAR), __ldcg(ad + LMC_ADAPT_HBAR),
-                 __ldcg(ad + LMC_ADAPT_COUNT), __ldcg(ad + LMC_ADAPT_MU)};
-      WelfordScalars wel{__ldcg(ad + LMC_ADAPT_W_FG), __ldcg(ad + LMC_ADAPT_W_BG),
-                         (long long)__ldcg(ad + LMC_ADAPT_NSAMPLES), (long long)__ldcg(ad + LMC_ADAPT_WINDOW)};
+      // (the adaptation scalars are loaded in the epilogue, where they are used: holding 18 registers of them across
+      //  the whole tree made the compiler spill hot tree state instead)
       const uint64_t seed = (a.rng.mode == LMC_RNG_PHILOX) ? a.rng.seeds[chain] : 0ull;
 
       const long long it = a.iter0 + t;  // BaseHMC.iter_count
@@ -208,7 +208,8 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
         status |= LMC_STATUS_BAD_INITIAL_ENERGY;
         dead = true;
       } else {
-        double eps = exp_cold(adapt_step ? da.log_step : da.log_bar);  // step_sizes.py:58-69
+        double eps = exp_cold(__ldcg(a.adapt + (size_t)chain * LMC_ADAPT_STRIDE +
+                                     (adapt_step ? LMC_ADAPT_LOG_STEP : LMC_ADAPT_LOG_BAR)));  // step_sizes.py:58-69
         if (a.step_size_override) eps = __ldg(a.step_size_override + chain);  // step_rand hook, base_hmc.py:154-155
 
         double accept_stat, stat_a, stat_b, stat_energy, stat_energy_error, stat_c, stat_logp;
@@ -344,6 +345,11 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
         }
 
         // ---- step_adapt.update(accept_stat, adapt_step)  (step_sizes.py:71-92) ---------------------------------
+        double* const ad = a.adapt + (size_t)chain * LMC_ADAPT_STRIDE;
+        DualAvg da{__ldcg(ad + LMC_ADAPT_LOG_STEP), __ldcg(ad + LMC_ADAPT_LOG_BAR), __ldcg(ad + LMC_ADAPT_HBAR),
+                   __ldcg(ad + LMC_ADAPT_COUNT), __ldcg(ad + LMC_ADAPT_MU)};
+        WelfordScalars wel{__ldcg(ad + LMC_ADAPT_W_FG), __ldcg(ad + LMC_ADAPT_W_BG),
+                           (long long)__ldcg(ad + LMC_ADAPT_NSAMPLES), (long long)__ldcg(ad + LMC_ADAPT_WINDOW)};
         if (adapt_step) dual_average_update(da, accept_stat, a.target_accept, a.gamma, a.k, a.t0);
         // ---- potential.update(end.q, end.q_grad, tune)  (quadpotential.py:231-245, 322-338) --------------------
         if (tune && a.adapt_mass) {
@@ -353,6 +359,8 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
         }
 
         // ---- outputs: trace[:, i] = q (sampling.py:513) and the stats dict (base_hmc.py:185-188) ----------------
+        double* const trow = trace_row();
+        double* const srow = stats_row();
 #pragma unroll
         for (int k = 0; k < NP; ++k) {
           const int j = lane + k * G;
@@ -379,6 +387,7 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
         // ---- write the chain's state back (its next transition may run on another SM) ---------------------------
         store_row<G, NP>(a.q + (size_t)chain * a.ld, lane, ldh, q);
         store_row<G, NP>(a.var + (size_t)chain * a.ld, lane, ldh, var);
+        group_barrier<G>();  // every thread has read the adaptation scalars (this epilogue) before lane 0 overwrites them
         if (lane == 0) {
           ad[LMC_ADAPT_LOG_STEP] = da.log_step;
           ad[LMC_ADAPT_LOG_BAR] = da.log_bar;
@@ -394,6 +403,8 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
     }  // !dead
     if (dead) {  // a stopped chain: its remaining rows are NaN
       const double nan = CUDART_NAN;
+      double* const trow = trace_row();
+      double* const srow = stats_row();
       for (int e = lane; e < D; e += G) trow[e] = nan;
       if (lane == 0)
         for (int s = 0; s < LMC_NSTATS; ++s) srow[s] = nan;

@@ -95,8 +95,11 @@ __global__ void __launch_bounds__(G, MINCTAS) sampler_lean_kernel(const lmc_samp
     bool dead = ((unsigned)chain & kDeadBit) != 0u;
     chain &= 0x7fffffff;
     const size_t row = (size_t)chain * a.n_trans + t;
-    double* const srow = a.stats + row * LMC_NSTATS;
-    double* const trow = a.trace + (size_t)chain * a.trace_chain_stride + (size_t)t * a.trace_draw_stride;
+    // output rows of this unit: computed where they are written (epilogue / dead-chain fill), not held across the tree
+    auto stats_row = [&]() -> double* { return a.stats + row * LMC_NSTATS; };
+    auto trace_row = [&]() -> double* {
+      return a.trace + (size_t)chain * a.trace_chain_stride + (size_t)t * a.trace_draw_stride;
+    };
     int status = 0;
 
     if (!dead) {
@@ -110,11 +113,8 @@ __global__ void __launch_bounds__(G, MINCTAS) sampler_lean_kernel(const lmc_samp
 #pragma unroll
         for (int k = 0; k < NP; ++k) s_var[k * G] = var[k];
       }
-      double* const ad = a.adapt + (size_t)chain * LMC_ADAPT_STRIDE;
-      DualAvg da{__ldcg(ad + LMC_ADAPT_LOG_STEP), __ldcg(ad + LMC_ADAPT_LOG_BAR), __ldcg(ad + LMC_ADAPT_HBAR),
-                 __ldcg(ad + LMC_ADAPT_COUNT), __ldcg(ad + LMC_ADAPT_MU)};
-      WelfordScalars wel{__ldcg(ad + LMC_ADAPT_W_FG), __ldcg(ad + LMC_ADAPT_W_BG),
-                         (long long)__ldcg(ad + LMC_ADAPT_NSAMPLES), (long long)__ldcg(ad + LMC_ADAPT_WINDOW)};
+      // (the adaptation scalars are loaded in the epilogue, where they are used: holding 18 registers of them across
+      //  the whole tree made the compiler spill hot tree state instead)
       const uint64_t seed = (a.rng.mode == LMC_RNG_PHILOX) ? a.rng.seeds[chain] : 0ull;
       const long long it = a.iter0 + t;
       const bool tune = it < a.n_tune;
@@ -164,7 +164,8 @@ __global__ void __launch_bounds__(G, MINCTAS) sampler_lean_kernel(const lmc_samp
         status |= LMC_STATUS_BAD_INITIAL_ENERGY;
         dead = true;
       } else {
-        double eps = exp_cold(adapt_step ? da.log_step : da.log_bar);
+        double eps = exp_cold(__ldcg(a.adapt + (size_t)chain * LMC_ADAPT_STRIDE +
+                                     (adapt_step ? LMC_ADAPT_LOG_STEP : LMC_ADAPT_LOG_BAR)));
         if (a.step_size_override) eps = __ldg(a.step_size_override + chain);
         bool diverging = false, reached_max = false;
 
@@ -392,6 +393,11 @@ __global__ void __launch_bounds__(G, MINCTAS) sampler_lean_kernel(const lmc_samp
 #pragma unroll
         for (int k = 0; k < NP; ++k) q[k] = sc.vec(tvid(tail, T_PROPQ))[k * G];  // hmc_step.end.q
 
+        double* const ad = a.adapt + (size_t)chain * LMC_ADAPT_STRIDE;
+        DualAvg da{__ldcg(ad + LMC_ADAPT_LOG_STEP), __ldcg(ad + LMC_ADAPT_LOG_BAR), __ldcg(ad + LMC_ADAPT_HBAR),
+                   __ldcg(ad + LMC_ADAPT_COUNT), __ldcg(ad + LMC_ADAPT_MU)};
+        WelfordScalars wel{__ldcg(ad + LMC_ADAPT_W_FG), __ldcg(ad + LMC_ADAPT_W_BG),
+                           (long long)__ldcg(ad + LMC_ADAPT_NSAMPLES), (long long)__ldcg(ad + LMC_ADAPT_WINDOW)};
         if (adapt_step) dual_average_update(da, accept_stat, a.target_accept, a.gamma, a.k, a.t0);
         if (tune && a.adapt_mass) {
           const size_t off = (size_t)chain * a.ld;
@@ -402,6 +408,8 @@ __global__ void __launch_bounds__(G, MINCTAS) sampler_lean_kernel(const lmc_samp
                                 var, wel, a.window_multiplier);
           store_row<G, NP>(a.var + off, lane, ldh, var);
         }
+        double* const trow = trace_row();
+        double* const srow = stats_row();
 #pragma unroll
         for (int k = 0; k < NP; ++k) {
           const int j = lane + k * G;
@@ -425,6 +433,7 @@ __global__ void __launch_bounds__(G, MINCTAS) sampler_lean_kernel(const lmc_samp
           srow[LMC_STAT_REACHED_MAX_TREEDEPTH] = reached_max ? 1.0 : 0.0;
         }
         store_row<G, NP>(a.q + (size_t)chain * a.ld, lane, ldh, q);
+        __syncthreads();  // every thread has read the adaptation scalars (this epilogue) before lane 0 overwrites them
         if (lane == 0) {
           ad[LMC_ADAPT_LOG_STEP] = da.log_step;
           ad[LMC_ADAPT_LOG_BAR] = da.log_bar;
@@ -440,6 +449,8 @@ __global__ void __launch_bounds__(G, MINCTAS) sampler_lean_kernel(const lmc_samp
     }
     if (dead) {
       const double nan = CUDART_NAN;
+      double* const trow = trace_row();
+      double* const srow = stats_row();
       for (int e = lane; e < D; e += G) trow[e] = nan;
       if (lane == 0)
         for (int s = 0; s < LMC_NSTATS; ++s) srow[s] = nan;
