@@ -15,6 +15,8 @@ from . import _lib as L
 import os as _os
 _DIRECT_CB = _os.environ.get("LMC_DIRECT_CB", "1") == "1"     # experiment switch (callback output buffers, see CallbackRun)
 
+_GRAPH_RES = {}   # device -> (side stream, CUDA-graph memory pool) of callback mode
+
 # launches of this library's kernels enqueued by this process (bench.py reports the count inside its timed region)
 LAUNCH_COUNT = {"kernels": 0}
 
@@ -291,10 +293,12 @@ class CallbackRun:
         self.n_evals += 1
         LAUNCH_COUNT["kernels"] += 1
 
-    def run(self, cuda_graph=False, iters_per_graph=8, poll=4):
+    def run(self, cuda_graph=False, iters_per_graph=None, poll=4):
         dev = self.chains.device
         with torch.cuda.device(dev):
             self.begin()
+            if iters_per_graph is None:
+                iters_per_graph = int(_os.environ.get("LMC_CB_GRAPH_ITERS", "8"))
             if cuda_graph:
                 self._run_graphed(iters_per_graph)
             else:
@@ -316,14 +320,19 @@ class CallbackRun:
 
     def _run_graphed(self, iters_per_graph):
         dev = self.chains.device
-        side = torch.cuda.Stream(device=dev)
+        # one side stream and ONE graph memory pool per device, shared by every capture of this process: a fresh
+        # pool per graph means cudaMalloc at capture and a synchronising cudaFree when the graph dies, every call
+        key = str(dev)
+        if key not in _GRAPH_RES:
+            _GRAPH_RES[key] = (torch.cuda.Stream(device=dev), torch.cuda.graph_pool_handle())
+        side, pool = _GRAPH_RES[key]
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):       # warm the callback up outside capture (lazy init, autotune, allocations)
             evaluate_callback(self.callback, self.q_eval[:, :self.chains.ndim])
         torch.cuda.current_stream(dev).wait_stream(side)
         graph = torch.cuda.CUDAGraph()
         before = self.n_evals
-        with torch.cuda.graph(graph):
+        with torch.cuda.graph(graph, pool=pool):
             for _ in range(iters_per_graph):
                 self.iteration()
         self.n_evals = before
