@@ -6,7 +6,8 @@
 Workload (default "headline", the north star's target workload): NUTS, 1024 chains per GPU,
 1000-dim diagonal Gaussian (sigma_i = 10^linspace(-.5,.5)), QuadPotentialDiagAdapt + dual averaging, max_treedepth 10,
 in-kernel Philox randomness.  One STEP = one launch of the sampler kernel = `--trans-per-step` consecutive NUTS
-transitions of every chain (momentum draw, tree building, both adaptations, trace + statistics written to HBM),
+transitions of every chain (default 16: the block size littlemcmc_b200.sample() uses at this problem size; the default
+25 steps after 5 warm-up steps cover iterations 80..480 of one run, 120 of them tuning) (momentum draw, tree building, both adaptations, trace + statistics written to HBM),
 continuing one run: the first `--tune` transitions tune.  Only useful leapfrogs (sum of the `tree_size` statistic over
 the timed steps) are counted.  Weak scaling: every GPU runs its own block of chains, no collective while sampling,
 one NCCL all-gather of the last step's draws afterwards (timed separately, reported as `allgather_ms`).
@@ -368,11 +369,12 @@ def run_gpu_arm(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=25)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS))
-    ap.add_argument("--trans-per-step", type=int, default=10)
+    ap.add_argument("--trans-per-step", type=int, default=16,
+                    help="transitions per launch; 16 = the block sample() itself uses at 1024 chains x 1000 dimensions")
     ap.add_argument("--chains", type=int, default=0, help="override chains per GPU")
     ap.add_argument("--cpu-trans", type=int, default=0, help="transitions per CPU-baseline chain (0 = bounded default)")
     ap.add_argument("--no-cpu", action="store_true")

@@ -105,8 +105,12 @@ def sample(logp_dlogp_func, model_ndim, draws=1000, tune=1000, step=None, init="
 
     keep_from = int(tune) if discard_tuned_samples else 0
     n_keep = T - keep_from
+    block_kept_on_device = block
     if block is None:
         block = max(1, min(T, (1 << 27) // max(1, chains * D * 8)))
+        # kept draws that stay on the device need no staging: one launch for all of them (every launch boundary costs
+        # a drain -- the last transitions of a block run on a partly idle GPU); 2^31 scheduler tickets per launch
+        block_kept_on_device = max(1, min(T, ((1 << 31) - 1) // max(1, chains))) if callback is None else block
     if return_device:
         trace_out = torch.empty(chains, n_keep, D, dtype=torch.float64, device=dev)
         host_trace = None
@@ -125,10 +129,10 @@ def sample(logp_dlogp_func, model_ndim, draws=1000, tune=1000, step=None, init="
     interrupted = False
     try:
         while done < T:
-            n = min(block, T - done)
+            kept = done >= keep_from
+            n = min(block_kept_on_device if (kept and return_device) else block, T - done)
             if done < keep_from < done + n:
                 n = keep_from - done                       # a block never straddles the discard boundary
-            kept = done >= keep_from
             if kept and return_device:
                 tr_view = trace_out[:, done - keep_from:done - keep_from + n]
                 _, st = step._run(n, int(tune), trace=tr_view)
