@@ -5,7 +5,7 @@ kernels) and `distributed` (chain sharding over the GPUs of a node).
 """
 __version__ = "0.1.0"
 
-from . import diagnostics, distributed, targets  # noqa: F401
+from . import diagnostics, distributed, interop, targets  # noqa: F401
 from .hmc import HamiltonianMC  # noqa: F401
 from .nuts import NUTS  # noqa: F401
 from .quadpotential import (  # noqa: F401

@@ -141,3 +141,23 @@ def test_dense_potential_validation_and_factory():
     for init in ("adapt_full", "jitter+adapt_full"):
         start, step = lmc.init_nuts(lmc.targets.StdNormal(3), 3, init=init, random_seed=4)
         assert isinstance(step.potential, lmc.QuadPotentialFullAdapt) and start.shape == (3,)
+
+
+def test_arviz_export_dicts():
+    """The reference cookbook's `arviz_from_littlemcmc` layout (docs/tutorials/framework_cookbook.rst:199-205)."""
+    import littlemcmc_b200 as lmc
+    trace = np.arange(2 * 5 * 3, dtype="d").reshape(2, 5, 3)
+    stats = {"depth": np.ones((2, 5, 1), dtype=np.int64), "diverging": np.zeros((2, 5, 1), dtype=bool)}
+    posterior, sample_stats = lmc.interop.to_arviz_dict(trace, stats)
+    assert posterior["x"].shape == (2, 5, 3) and np.array_equal(posterior["x"], trace)
+    assert sample_stats["depth"].shape == (2, 5) and sample_stats["depth"].dtype == np.int64
+    assert sample_stats["diverging"].dtype == bool
+    with pytest.raises(ValueError):
+        lmc.interop.to_arviz_dict(trace[0], stats)
+    with pytest.raises(ValueError):
+        lmc.interop.to_arviz_dict(trace, {"depth": np.ones((2, 4, 1))})
+    try:
+        import arviz  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError, match="arviz"):
+            lmc.interop.arviz_from_littlemcmc(trace, stats)
