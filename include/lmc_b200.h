@@ -157,7 +157,9 @@ typedef struct lmc_sampler_args {
   void* workspace;     /* >= lmc_workspace_bytes(...) bytes, 16-byte aligned                                */
   int64_t workspace_bytes;
   void* stream;        /* cudaStream_t                                                                      */
-  int32_t tune_group;  /* 0 = library picks threads-per-chain; else force 32/64/128/256/512 (experiments)   */
+  int32_t tune_group;  /* 0 = library picks threads-per-chain; > 0: force 32/64/128/256/512/1024 with the
+                          register-resident kernel; < 0: force -tune_group (64/128/256) with the lean NUTS kernel
+                          (experiments and tests)                                                            */
   int32_t tune_smem_vecs; /* -1 = library picks how many scratch vectors live in shared memory; else force  */
   int32_t tune_max_slots; /* 0 = library picks the number of resident chain slots; else cap it              */
   int32_t reserved3;

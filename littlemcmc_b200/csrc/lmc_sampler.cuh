@@ -1,11 +1,12 @@
 // lmc_nuts_sample / lmc_hmc_sample: whole MCMC transitions (momentum draw, initial state, trajectory, both
 // adaptations, trace + statistics) for thousands of independent chains in ONE launch.
 //
-// Execution model.  A chain is owned by a thread group (lmc_device.cuh) for all `n_trans` transitions of the
-// call; its live phase-space point (q, p, grad), its mass-matrix diagonal and every tree scalar stay in
-// registers for the whole call.  Chains never synchronise with each other, so there is no lock-step loss: a
-// chain that needs 1023 leapfrogs for a draw does not hold up one that needs 3.  The grid is persistent
-// (`n_slots` resident groups striding over the chains) so the tree scratch is per resident slot, not per chain.
+// Execution model.  The unit of work is one transition of one chain, run by a thread group (lmc_device.cuh) that keeps
+// the chain's live phase-space point (q, p, grad), its mass-matrix diagonal and every tree scalar in registers for
+// the whole transition.  Chains never synchronise with each other, so there is no lock-step loss: a chain that needs
+// 1023 leapfrogs for a draw does not hold up one that needs 3.  The grid is persistent (one resident group per
+// "slot", fed by a FIFO of chains, see the scheduler below), so the tree scratch is per resident slot, not per chain.
+// For 513..1024 dimensions the default is the lean variant of this kernel (lmc_sampler_lean.cuh).
 //
 // NUTS tree (reference nuts.py:251-435) is built with the iterative binary-counter stack of SURVEY.md A.1:
 // leaf i is merged with stack level 0,1,.. for every trailing 1-bit of i, which visits merges in exactly the
