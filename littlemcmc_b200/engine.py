@@ -395,9 +395,12 @@ class DenseRun:
         self.max_iters = 2 * int(n_trans) * per + 4
         self.n_grad_evals = self.n_vel_evals = 0
 
-    def _subset(self, mask_host):
-        """-> None when every chain is selected, else an int64 device index tensor."""
-        if mask_host.all():
+    def _subset(self, mask_host, all_above=1.0):
+        """-> None (= every chain) when at least the fraction `all_above` of the chains is selected, else an int64
+        device index tensor.  Potentials whose operations are one library GEMM over a matrix shared by all chains
+        set `_all_rows_above` < 1: serving rows nobody asked for is cheaper than gathering / scattering the rest
+        (a chain only reads a result buffer in the phase in which it asked for it)."""
+        if mask_host.all() or mask_host.mean() >= all_above:
             return None
         return torch.as_tensor(np.nonzero(mask_host)[0], device=self.chains.device)
 
@@ -419,8 +422,9 @@ class DenseRun:
                 m_grad, m_vel = (need & L.NEED_GRAD) != 0, (need & L.NEED_VEL) != 0
                 if m_upd.any():                           # potential.update first: the momentum draw uses the new matrix
                     pot._update_rows(torch.as_tensor(np.nonzero(m_upd)[0], device=dev), self.chains.q)
+                lib_all = float(getattr(pot, "_all_rows_above", 1.0))
                 if m_mom.any():
-                    pot._momentum_rows(self._subset(m_mom), self.n_eval, self.p0_eval)
+                    pot._momentum_rows(self._subset(m_mom, lib_all), self.n_eval, self.p0_eval)
                 if m_grad.any():
                     idx = self._subset(m_grad)
                     qs = self.q_eval[:, :D] if idx is None else self.q_eval[idx][:, :D]
@@ -433,7 +437,7 @@ class DenseRun:
                         self.logp_eval[idx] = logp
                     self.n_grad_evals += 1
                 if m_vel.any():
-                    pot._velocity_rows(self._subset(m_vel), self.x_eval, self.v_eval)
+                    pot._velocity_rows(self._subset(m_vel, lib_all), self.x_eval, self.v_eval)
                     self.n_vel_evals += 1
                 self.c.base.stream = stream.cuda_stream
                 L.check(self.lib.lmc_dense_advance(self.kind, C.byref(self.c)), "lmc_dense_advance")

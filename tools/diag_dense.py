@@ -27,6 +27,12 @@ pot._velocity_rows = timed("velocity", pot._velocity_rows)
 pot._momentum_rows = timed("momentum", pot._momentum_rows)
 engine.evaluate_callback = timed("gradient", engine.evaluate_callback)
 step = lmc.NUTS(target, D, potential=pot, max_treedepth=8)
+lmc.sample(target, D, draws=1, tune=2, step=step, chains=Cn, start=np.zeros(D), random_seed=list(range(Cn)),
+           discard_tuned_samples=False, return_device=True)      # warm-up: library page-in, cuBLAS / cuSOLVER handles
+T.clear()
+iters = collections.Counter()
+_adv = engine.L.load().lmc_dense_advance
+torch.cuda.synchronize()
 t0 = time.perf_counter()
 tr, st = lmc.sample(target, D, draws=5, tune=10, step=step, chains=Cn, start=np.zeros(D), random_seed=list(range(Cn)),
                     discard_tuned_samples=False, return_device=True)
