@@ -375,6 +375,10 @@ class DenseRun:
         self.n_eval, self.p0_eval = z(Cn, ld), z(Cn, ld)
         self.need = torch.zeros(Cn, dtype=torch.int32, device=dev)
         self.need_host = torch.zeros(Cn, dtype=torch.int32).pin_memory()
+        # index lists travel through pinned staging (a pageable H2D copy blocks the host for tens of microseconds)
+        self._idx_pinned = [torch.zeros(Cn, dtype=torch.int64).pin_memory() for _ in range(4)]
+        self._idx_dev = [torch.zeros(Cn, dtype=torch.int64, device=dev) for _ in range(4)]
+        self._idx_slot = 0
         self.n_running = torch.zeros(1, dtype=torch.int32, device=dev)
         self.c = L.DenseArgs()
         with torch.cuda.device(dev):
@@ -402,7 +406,13 @@ class DenseRun:
         (a chain only reads a result buffer in the phase in which it asked for it)."""
         if mask_host.all() or mask_host.mean() >= all_above:
             return None
-        return torch.as_tensor(np.nonzero(mask_host)[0], device=self.chains.device)
+        idx = np.nonzero(mask_host)[0]
+        k = self._idx_slot
+        self._idx_slot = (k + 1) % 4        # four lists per iteration at most; stream order protects their reuse
+        self._idx_pinned[k].numpy()[:idx.size] = idx
+        out = self._idx_dev[k][:idx.size]
+        out.copy_(self._idx_pinned[k][:idx.size], non_blocking=True)
+        return out
 
     def run(self):
         dev, D = self.chains.device, self.chains.ndim
@@ -422,6 +432,7 @@ class DenseRun:
                 m_grad, m_vel = (need & L.NEED_GRAD) != 0, (need & L.NEED_VEL) != 0
                 if m_upd.any():                           # potential.update first: the momentum draw uses the new matrix
                     pot._update_rows(torch.as_tensor(np.nonzero(m_upd)[0], device=dev), self.chains.q)
+                self._idx_slot = 0
                 lib_all = float(getattr(pot, "_all_rows_above", 1.0))
                 if m_mom.any():
                     pot._momentum_rows(self._subset(m_mom, lib_all), self.n_eval, self.p0_eval)

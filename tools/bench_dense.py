@@ -89,3 +89,5 @@ for name, mk, n_trans, tune in (("QuadPotentialFull (shared matrix)", lambda: lm
     del step, tr, st
     torch.cuda.empty_cache()
 print(json.dumps(out))
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(out, open("gpurun_out/dense_bench.json", "w"))
