@@ -82,8 +82,14 @@ static __global__ void sched_init_kernel(void* workspace, int n_chains) {
 #ifndef LMC_MC_256_2
 #define LMC_MC_256_2 2
 #endif
+#ifndef LMC_MC_32_1
+#define LMC_MC_32_1 4
+#endif
+#ifndef LMC_MC_32_2
+#define LMC_MC_32_2 4
+#endif
 #define LMC_SHAPES(X) \
-  X(32, 1, 4) X(32, 2, 4) X(32, 4, 3) X(64, 4, 4) X(64, 8, 4) X(128, 2, 4) X(128, 4, LMC_MC_128_4) \
+  X(32, 1, LMC_MC_32_1) X(32, 2, LMC_MC_32_2) X(32, 4, 3) X(64, 4, 4) X(64, 8, 4) X(128, 2, 4) X(128, 4, LMC_MC_128_4) \
   X(256, 2, LMC_MC_256_2) X(256, 4, 1) X(512, 2, 1) X(512, 4, 1) X(1024, 4, 1)
 
 template <int G, int NP>
