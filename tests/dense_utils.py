@@ -129,7 +129,6 @@ def gpu_run_dense_transitionwise(case, ora, device="cuda:0"):
     """Every transition from the oracle's pre-state.  -> (q [C,T,D], adapt [C,T,5], stats [C,T,NSTATS],
     pots: list[T] of per-chain potential state dicts, status)"""
     import torch
-    from littlemcmc_b200 import _lib as L
     from littlemcmc_b200 import engine
     from tests import parity_utils as pu
     normals, uniforms, _ = ora["tapes"]

@@ -5,7 +5,6 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from oracle import lmc_oracle as orc
 from tests import parity_utils as pu
 
 pytestmark = pytest.mark.gpu

@@ -3,7 +3,7 @@ import sys, time, collections
 import numpy as np, torch
 sys.path.insert(0, ".")
 import littlemcmc_b200 as lmc
-from littlemcmc_b200 import engine, _lib as L
+from littlemcmc_b200 import engine
 from littlemcmc_b200.targets import TorchBatched
 Cn, D = int(sys.argv[1]), int(sys.argv[2])
 dev = torch.device("cuda", 0)
@@ -30,8 +30,6 @@ step = lmc.NUTS(target, D, potential=pot, max_treedepth=8)
 lmc.sample(target, D, draws=1, tune=2, step=step, chains=Cn, start=np.zeros(D), random_seed=list(range(Cn)),
            discard_tuned_samples=False, return_device=True)      # warm-up: library page-in, cuBLAS / cuSOLVER handles
 T.clear()
-iters = collections.Counter()
-_adv = engine.L.load().lmc_dense_advance
 torch.cuda.synchronize()
 t0 = time.perf_counter()
 tr, st = lmc.sample(target, D, draws=5, tune=10, step=step, chains=Cn, start=np.zeros(D), random_seed=list(range(Cn)),

@@ -3,7 +3,7 @@ import sys, time
 import numpy as np, torch
 sys.path.insert(0, ".")
 import littlemcmc_b200 as lmc
-from littlemcmc_b200 import _lib as L, engine
+from littlemcmc_b200 import _lib as L
 C_, D, tps = 1024, 1000, int(sys.argv[1]) if len(sys.argv) > 1 else 10
 flush_on = (sys.argv[2] != "noflush") if len(sys.argv) > 2 else True
 dev = torch.device("cuda", 0)

@@ -1,7 +1,6 @@
 """Scratch throughput probe (not the contract bench): NUTS on a diagonal Gaussian with in-kernel Philox, sweeping
 launch knobs.  Usage: python tools/quick_bench.py [C] [D] [n_trans] [group,group,...] [smem,smem,...]"""
 import sys
-import time
 
 import numpy as np
 import torch
