@@ -161,6 +161,24 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Multi-GPU runs: pin this rank to the CPU cores NVML reports as local to its GPU, so that the pinned host buffers
+    of the end-to-end path are allocated (first touch) on the GPU's own NUMA node and its D2H traffic does not cross the
+    socket interconnect.  Best effort: silently keeps the inherited affinity when NVML or the OS call is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 # ---- GPU arm -----------------------------------------------------------------------------------------------------------
 def run_gpu_arm(args, wl):
     import torch
@@ -177,6 +195,8 @@ def run_gpu_arm(args, wl):
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
+    if world > 1 and not args.no_affinity:
+        bind_to_gpu_numa_node(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -327,7 +347,7 @@ def run_gpu_arm(args, wl):
     # -- CPU baseline on this box's host cores (bounded sample) ----------------------------------------------------------------
     cores = os.cpu_count() or 1
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:                          # the CPU baseline is an N=1 line
         n_cpu = args.cpu_trans or 3000
         _, _, cpu_rate = cpu_reference_step(kind, D, max_depth, n_cpu, cores, 4242)
         cpu = {"value": cpu_rate, "unit": "leapfrog-steps/s", "cores": cores, "kind": "port",
@@ -378,6 +398,7 @@ def main():
     ap.add_argument("--chains", type=int, default=0, help="override chains per GPU")
     ap.add_argument("--cpu-trans", type=int, default=0, help="transitions per CPU-baseline chain (0 = bounded default)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-affinity", action="store_true", help="N>1: do not bind ranks to their GPU's NUMA node")
     ap.add_argument("--logp", default="fused", choices=["fused", "torch", "torch-graph"],
                     help="fused: density inside the kernel; torch: batched torch op between launches (callback mode)")
     ap.add_argument("--group", type=int, default=0)
