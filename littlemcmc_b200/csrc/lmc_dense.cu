@@ -821,7 +821,7 @@ extern "C" int lmc_dense_matvec(const int32_t* idx, int32_t n_idx, const double*
 extern "C" int lmc_dense_cov_update(const int32_t* idx, int32_t n_idx, int32_t ndim, int64_t ld, int64_t lda,
                                     const double* x, double* mean_fg, double* raw_fg, double* mean_bg, double* raw_bg,
                                     double* nsamp, double* cov, void* stream) {
-  if (!x || !mean_fg || !raw_fg || !mean_bg || !raw_bg || !nsamp || !cov || ndim < 1 || n_idx < 0 || ld < ndim ||
+  if (!x || !mean_fg || !raw_fg || !mean_bg || !raw_bg || !nsamp || ndim < 1 || n_idx < 0 || ld < ndim ||
       lda < ndim)
     return LMC_ERR_BADARG;
   if (n_idx == 0) return LMC_OK;

@@ -310,7 +310,7 @@ class QuadPotentialFullAdapt(_DenseBase):
             sel32.record_stream(torch.cuda.current_stream(self._dev))
             if flag:                                                      # _update_from_weightvar (:520-526)
                 chol, info = torch.linalg.cholesky_ex(self._cov_all[sel][:, :, :D])
-                ok = info == 0
+                ok = (info == 0) & torch.isfinite(chol).all(dim=2).all(dim=1)   # LinAlgError / ValueError in scipy (:524)
                 if not bool(ok.all()):
                     self._chol_error = "Cholesky failed for chain(s) %s" % sel[~ok].tolist()[:8]
                 self._chol_all[sel[ok]] = chol[ok]
@@ -326,6 +326,17 @@ class QuadPotentialFullAdapt(_DenseBase):
             self._previous_update_all[switch] = self._n_samples_all[switch]
             self._window_all[switch] = (self._window_all[switch] * self._adaptation_window_multiplier).astype(np.int64)
         self._n_samples_all[idx_h] += 1
+
+    def update(self, sample, grad, tune):
+        """reference quadpotential.py:528-554 for ONE sample: the reference's object-level API (its tests drive the
+        potential directly).  Applies to the last chain (the only one when the potential is not bound to a sampler);
+        the sampler itself updates all chains that finished a tuning transition at once (`_update_rows`)."""
+        if not tune:
+            return
+        x = self._single(sample)                      # (moves the state to the device on first use)
+        q = torch.zeros(self._nc, self._ld, dtype=torch.float64, device=self._dev)
+        q[-1, :self._n] = x
+        self._update_rows(torch.tensor([self._nc - 1], dtype=torch.int64, device=self._dev), q)
 
     def raise_ok(self, vmap=None):
         """reference quadpotential.py:556-559."""

@@ -186,3 +186,43 @@ def test_dense_integrator_matches_oracle_and_is_reversible():
                     state = step.integrator.step(-epsilon, state)
                 np.testing.assert_allclose(state.q, start.q, rtol=1e-5)
                 np.testing.assert_allclose(state.p, start.p, rtol=1e-5)
+
+
+def test_full_adapt_object_api_like_the_reference_tests():
+    """reference tests/test_quadpotential.py:158-223 driven through the object-level API (`random`, `update`,
+    `raise_ok`, `_cov`, `_previous_update`, `_adaptation_window`): test_full_adapt_sample_p, _update_window,
+    _adaptation_window, _not_invertible."""
+    import littlemcmc_b200 as lmc
+    # sample_p: momenta drawn with inverse-covariance m_inv have covariance m (5 sigma of the Wishart spread)
+    np.random.seed(4566)
+    m = np.array([[3.0, -2.0], [-2.0, 4.0]])
+    m_inv = np.linalg.inv(m)
+    var = np.array([[2 * m[0, 0], m[1, 0] * m[1, 0] + m[1, 1] * m[0, 0]],
+                    [m[0, 1] * m[0, 1] + m[1, 1] * m[0, 0], 2 * m[1, 1]]])
+    n_samples = 1000
+    pot = lmc.QuadPotentialFullAdapt(2, np.zeros(2), m_inv, 1)
+    sample_cov = np.cov([pot.random() for _ in range(n_samples)], rowvar=0)
+    assert np.all(np.abs(m - sample_cov) < 5 * np.sqrt(var / n_samples))
+    # update_window: the matrix is refreshed every 50th update only
+    np.random.seed(1123)
+    init_cov = np.array([[1.0, 0.02], [0.02, 0.8]])
+    pot = lmc.QuadPotentialFullAdapt(2, np.zeros(2), init_cov, 1, update_window=50)
+    for _ in range(49):
+        pot.update(np.random.randn(2), None, True)
+    assert np.allclose(pot._cov, init_cov)
+    pot.update(np.random.randn(2), None, True)
+    assert not np.allclose(pot._cov, init_cov)
+    # adaptation_window: the foreground estimator is swapped after `window` updates and the window doubles
+    np.random.seed(8978)
+    window = 10
+    pot = lmc.QuadPotentialFullAdapt(2, np.zeros(2), np.eye(2), 1, adaptation_window=window)
+    for _ in range(window + 1):
+        pot.update(np.random.randn(2), None, True)
+    assert pot._previous_update == window
+    assert pot._adaptation_window == window * pot._adaptation_window_multiplier
+    # not invertible: identical samples give a singular covariance; the error surfaces through raise_ok
+    pot = lmc.QuadPotentialFullAdapt(2, np.zeros(2), np.eye(2), 0, adaptation_window=window)
+    for _ in range(window + 1):
+        pot.update(np.ones(2), None, True)
+    with pytest.raises(ValueError):
+        pot.raise_ok(None)

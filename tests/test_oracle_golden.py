@@ -83,3 +83,22 @@ def test_dense_oracle_matches_reference(name):
             np.testing.assert_allclose(pot.cov, ref["final_cov"][c], rtol=1e-10)
             assert pot.n_samples == int(ref["final_n_samples"][c]) == int(case["tune"])
             assert pot.adaptation_window == int(ref["final_window"][c])
+
+
+def test_oracle_weighted_covariance_is_the_sample_covariance(ndim=10, seed=5432):
+    """reference tests/test_quadpotential.py:119-156 on the oracle's `_WeightedCovariance` restatement."""
+    np.random.seed(seed)
+    L = np.random.randn(ndim, ndim)
+    L[np.triu_indices_from(L, 1)] = 0.0
+    L[np.diag_indices_from(L)] = np.exp(L[np.diag_indices_from(L)])
+    cov = np.dot(L, L.T)
+    mean = np.random.randn(ndim)
+    samples = np.random.multivariate_normal(mean, cov, size=100)
+    est = orc.WelfordCov(ndim)
+    for s in samples:
+        est.add_sample(s, 1)
+    assert np.allclose(est.mean, samples.mean(0)) and np.allclose(est.current_covariance(), np.cov(samples, rowvar=0))
+    est2 = orc.WelfordCov(ndim, samples[:10].mean(0), np.cov(samples[:10], rowvar=0, bias=True), 10)
+    for s in samples[10:]:
+        est2.add_sample(s, 1)
+    assert np.allclose(est2.mean, samples.mean(0)) and np.allclose(est2.current_covariance(), np.cov(samples, rowvar=0))
