@@ -290,7 +290,10 @@ def run_gpu_arm(args, wl):
     # -- end to end through the public API with host buffers -----------------------------------------------------------------
     # One warm-up call with the SAME shapes first: sample() returns its trace in pinned host memory, which torch's
     # caching host allocator hands back without a new cudaHostAlloc once a block of that size has been freed.
-    n_e2e = args.steps * tps
+    # the same transitions as the timed steps, capped at 640 so that the pinned host trace stays small (5 GB at the
+    # headline size) whatever --steps is; bytes are reported per step of `tps` transitions
+    n_e2e = min(args.steps * tps, 640)
+    e2e_steps = n_e2e / float(tps)
     e2e_tune = min(tune, n_e2e // 2)
     start_host = torch.zeros(chains, D, dtype=torch.float64).pin_memory()
     step2 = make_step()
@@ -323,8 +326,8 @@ def run_gpu_arm(args, wl):
     t0 = time.perf_counter()
     e2e_call(17, discard=True)
     e2e_default_s = time.perf_counter() - t0
-    h2d = (chains * D * 8 + chains * 8) / args.steps
-    d2h = (tr_h.nbytes + chains * n_e2e * L.NSTATS * 8) / args.steps
+    h2d = (chains * D * 8 + chains * 8) / e2e_steps
+    d2h = (tr_h.nbytes + chains * n_e2e * L.NSTATS * 8) / e2e_steps
 
     if rank != 0:
         if world > 1:
