@@ -290,9 +290,9 @@ def run_gpu_arm(args, wl):
     # -- end to end through the public API with host buffers -----------------------------------------------------------------
     # One warm-up call with the SAME shapes first: sample() returns its trace in pinned host memory, which torch's
     # caching host allocator hands back without a new cudaHostAlloc once a block of that size has been freed.
-    # the same transitions as the timed steps, capped at 640 so that the pinned host trace stays small (5 GB at the
-    # headline size) whatever --steps is; bytes are reported per step of `tps` transitions
-    n_e2e = min(args.steps * tps, 640)
+    # the same transitions as the timed steps, capped so that the pinned host trace stays below ~5 GB whatever --steps
+    # and the workload are (640 transitions at the headline size); bytes are reported per step of `tps` transitions
+    n_e2e = min(args.steps * tps, max(2 * tps, int(5.3e9 // (chains * D * 8))))
     e2e_steps = n_e2e / float(tps)
     e2e_tune = min(tune, n_e2e // 2)
     start_host = torch.zeros(chains, D, dtype=torch.float64).pin_memory()
