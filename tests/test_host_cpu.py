@@ -187,3 +187,17 @@ def test_bench_reference_arm_prints_the_contract_line():
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1"],
                          capture_output=True, text=True, timeout=120, cwd=root, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_bench_gpu_arm_fails_loudly_without_a_gpu():
+    """No CUDA device => the GPU arm exits non-zero and prints no result line (there is no CPU fallback to time)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("this check is for machines without a GPU")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "0", "--no-cpu"],
+                         capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode != 0
+    assert '"value"' not in out.stdout
