@@ -201,3 +201,39 @@ def test_bench_gpu_arm_fails_loudly_without_a_gpu():
                          capture_output=True, text=True, timeout=300, cwd=root)
     assert out.returncode != 0
     assert '"value"' not in out.stdout
+
+
+def test_ctypes_mirrors_have_the_c_layout(tmp_path):
+    """sizeof / offsetof of every struct in include/lmc_b200.h as a C compiler lays them out == the ctypes mirrors in
+    littlemcmc_b200/_lib.py (the header is plain C: it must compile with gcc, no CUDA headers)."""
+    import ctypes as C
+    import subprocess
+    from littlemcmc_b200 import _lib as L
+    structs = {"lmc_target": L.Target, "lmc_rng": L.Rng, "lmc_sampler_args": L.SamplerArgs,
+               "lmc_callback_args": L.CallbackArgs, "lmc_dense_args": L.DenseArgs}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "lmc_b200.h"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append('  printf("%s sizeof %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('  printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['  printf("abi %d nstats %d adapt_stride %d\\n", LMC_ABI_VERSION, LMC_NSTATS, LMC_ADAPT_STRIDE);',
+              "  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                   check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    seen = 0
+    for row in out:
+        parts = row.split()
+        if len(parts) == 3 and parts[1] == "sizeof":
+            assert C.sizeof(structs[parts[0]]) == int(parts[2]), row
+            seen += 1
+        elif len(parts) == 3 and parts[0] in structs:
+            assert getattr(structs[parts[0]], parts[1]).offset == int(parts[2]), row
+            seen += 1
+        elif parts and parts[0] == "abi":
+            assert (int(parts[1]), int(parts[3]), int(parts[5])) == (L.ABI_VERSION, L.NSTATS, L.ADAPT_STRIDE)
+            seen += 1
+    assert seen > 70
