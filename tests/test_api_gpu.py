@@ -285,3 +285,21 @@ def test_step_rand_through_the_api():
     assert not np.array_equal(out[0][0], out[2][0])                      # and the hook matters
     # halving every step size lengthens the trees
     assert out[0][1]["tree_size"].mean() > out[2][1]["tree_size"].mean()
+
+
+def test_device_streams_are_the_documented_philox_function():
+    """The per-chain random streams of the kernels (dumped by lmc_rng_fill; the sampler kernels consume exactly these:
+    test_philox_mode_equals_tape_mode) are the function documented in lmc_device.cuh and restated in oracle/philox.py,
+    which passes Random123's known-answer vectors on the CPU: uniforms bit for bit, Box-Muller normals to libm accuracy."""
+    import torch
+    from littlemcmc_b200 import engine
+    from oracle import philox
+    seeds = [0, 1, 12345, 2 ** 40 + 7, 2 ** 63 + 11]
+    iter0, n_trans, D, u_stride = 3, 2, 37, 70
+    st = engine.seeds_tensor(np.array(seeds, dtype=np.uint64), torch.device("cuda", 0))
+    normals, uniforms = engine.rng_fill(st, D, iter0, n_trans, u_stride)
+    normals, uniforms = normals.cpu().numpy(), uniforms.cpu().numpy()
+    for c, seed in enumerate(seeds):
+        for t in range(n_trans):
+            assert np.array_equal(uniforms[c, t], philox.uniforms(seed, iter0 + t, u_stride)), (seed, t)
+            np.testing.assert_allclose(normals[c, t], philox.normals(seed, iter0 + t, D), rtol=1e-13, atol=1e-14)

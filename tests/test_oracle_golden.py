@@ -102,3 +102,19 @@ def test_oracle_weighted_covariance_is_the_sample_covariance(ndim=10, seed=5432)
     for s in samples[10:]:
         est2.add_sample(s, 1)
     assert np.allclose(est2.mean, samples.mean(0)) and np.allclose(est2.current_covariance(), np.cov(samples, rowvar=0))
+
+
+def test_philox_restatement_known_answers():
+    """Random123's known-answer vectors for philox4x32_10 (kat_vectors: counter, key -> output)."""
+    from oracle import philox
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = philox.philox4x32_10(ctr, key)
+        assert tuple(int(np.asarray(x).reshape(-1)[0]) for x in got) == want
+    u = philox.uniforms(12345, 7, 1000)
+    assert ((u > 0) & (u < 1)).all() and abs(u.mean() - 0.5) < 0.03
+    z = philox.normals(12345, 7, 1001)
+    assert z.shape == (1001,) and abs(z.mean()) < 0.15 and abs(z.std() - 1) < 0.1
