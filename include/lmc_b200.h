@@ -169,7 +169,10 @@ typedef struct lmc_sampler_args {
 int lmc_abi_version(void);
 
 /* Bytes of scratch lmc_nuts_sample / lmc_hmc_sample need for this problem (host call, no GPU work).
- * `kind`: 0 = NUTS, 1 = HMC; `tune_group` as in lmc_sampler_args.  Returns < 0 on unsupported sizes. */
+ * `kind`: 0 = NUTS, 1 = HMC; `tune_group` as in lmc_sampler_args.  `max_treedepth` here and in the other *_bytes
+ * functions is the SCRATCH depth: max(args.max_treedepth, args.early_max_treedepth) -- trees grow to the early cap
+ * during the first 200 tuning transitions even when it exceeds max_treedepth (nuts.py:205-208).  Returns < 0 on
+ * unsupported sizes. */
 int64_t lmc_workspace_bytes(int32_t kind, int32_t n_chains, int32_t ndim, int32_t max_treedepth,
                             int32_t tune_group);
 

@@ -101,6 +101,7 @@ class BaseHMC:
         override = None
         if self._step_rand is not None:
             override = self._apply_step_rand(self.iter_count < n_tune)
+        self._last_override = override
         common = dict(n_trans=n_trans, iter0=self.iter_count, n_tune=n_tune, params=self._params(), seeds=self._seeds,
                       tapes=tapes, trace=trace, stats=stats, step_size_override=override)
         if getattr(self.potential, "_dense", False):
@@ -169,7 +170,9 @@ class BaseHMC:
         st = stats_dev
         post = st[:, n_tune_in_block:, :]
         if post.shape[1]:
-            self._samples_after_tune += post.shape[1]
+            # counted over ALL chains, like the divergence / max-treedepth counters they are compared with (the
+            # reference's sequential path accumulates every chain into the same step object, base_hmc.py:164-183)
+            self._samples_after_tune += post.shape[0] * post.shape[1]
             self._num_divs_sample += int(post[:, :, L.STAT_DIVERGING].sum().item())
             self.step_adapt._tuned_stats.extend(post[-1, :, L.STAT_ACCEPT].cpu().tolist())
 
@@ -187,11 +190,13 @@ class BaseHMC:
             self._bind(n_chains)
         self._chains.set_position(q0a)
         n_tune = self.iter_count + 1 if self.tune else 0
+        # base_hmc.py:152-156: step.step_size is the step size THIS transition integrates with (current() before the
+        # dual-averaging update, after the step_rand hook); last chain, as the reference's sequential path leaves it
+        eps_used = float(self.step_adapt.current_all(bool(self.tune and self.adapt_step_size))[-1].item())
         tr, st = self._run(1, n_tune)
         self._check_status()
         self._account(st, 1 if self.tune else 0)
-        self.step_size = float(st[-1, 0, L.STAT_STEP_SIZE_BAR if not (self.tune and self.adapt_step_size)
-                                  else L.STAT_STEP_SIZE].item())
+        self.step_size = eps_used if self._last_override is None else float(self._last_override[-1].item())
         sd = {n: st[:, 0, c].cpu().numpy().astype(self.stats_dtypes[0][n]) for n, c in self._stat_columns.items()}
         if one_d:
             sd = {n: v[0] for n, v in sd.items()}

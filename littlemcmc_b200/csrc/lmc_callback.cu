@@ -88,9 +88,9 @@ __global__ void __launch_bounds__(cb_block<G>()) cb_advance_kernel(const lmc_cal
   sc.n_smem = 0;
   sc.lane = lane;
   StackScalars* const ss = &M->ss;
-  const int V_P = KIND == KIND_NUTS ? ws_vecs_nuts(a.max_treedepth) : 0;  // half-kicked momentum between launches
+  const int V_P = KIND == KIND_NUTS ? ws_vecs_nuts(scratch_depth(a)) : 0;  // half-kicked momentum between launches
   const int V_Q0 = 1;                                                     // HMC: the transition's start position
-  const int tail = vid_tail(a.max_treedepth);
+  const int tail = vid_tail(scratch_depth(a));
 
   const int D = a.ndim;
   const int ldh = (int)(a.ld >> 1);
@@ -392,12 +392,12 @@ static int cb_check(int kind, const lmc_callback_args* c, int* G, int* NP, size_
   }
   if (kind == KIND_NUTS) {
     if (a.max_treedepth < 1 || a.max_treedepth > kMaxDepth) return LMC_ERR_UNSUPPORTED;
-    if (a.early_max_treedepth < 0 || a.early_max_treedepth > a.max_treedepth) return LMC_ERR_UNSUPPORTED;
+    if (a.early_max_treedepth < 0 || a.early_max_treedepth > kMaxDepth) return LMC_ERR_UNSUPPORTED;
   } else if (a.max_steps < 1) {
     return LMC_ERR_BADARG;
   }
   if (!cb_pick_shape(a.ndim, G, NP)) return LMC_ERR_UNSUPPORTED;
-  *n_vecs = cb_vecs(kind, a.max_treedepth);
+  *n_vecs = cb_vecs(kind, scratch_depth(a));
   *vec_off = (size_t)a.n_chains * kMachineBytes;
   const size_t need = *vec_off + (size_t)a.n_chains * *n_vecs * (size_t)(*G * *NP) * sizeof(double2);
   if ((size_t)c->machine_bytes < need) return LMC_ERR_WORKSPACE;

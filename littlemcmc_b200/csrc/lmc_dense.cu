@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(dn_block<G>()) dn_advance_kernel(const lmc_den
   sc.n_smem = 0;
   sc.lane = lane;
   StackScalars* const ss = &M->ss;
-  const int MD = a.max_treedepth;
+  const int MD = scratch_depth(a);  // stack sized for both depth caps (lmc_tree.cuh)
   const int tail = dv_tail(MD);
   const int V_Q0 = 0;  // HMC: the transition's start position
 
@@ -625,12 +625,12 @@ static int dn_check(int kind, const lmc_dense_args* c, int* G, int* NP, size_t* 
   }
   if (kind == DK_NUTS) {
     if (a.max_treedepth < 1 || a.max_treedepth > kMaxDepth) return LMC_ERR_UNSUPPORTED;
-    if (a.early_max_treedepth < 0 || a.early_max_treedepth > a.max_treedepth) return LMC_ERR_UNSUPPORTED;
+    if (a.early_max_treedepth < 0 || a.early_max_treedepth > kMaxDepth) return LMC_ERR_UNSUPPORTED;
   } else if (a.max_steps < 1) {
     return LMC_ERR_BADARG;
   }
   if (!dn_pick_shape(a.ndim, G, NP)) return LMC_ERR_UNSUPPORTED;
-  *n_vecs = dn_vecs(kind, a.max_treedepth);
+  *n_vecs = dn_vecs(kind, scratch_depth(a));
   *vec_off = (size_t)a.n_chains * kDnMachineBytes;
   const size_t need = *vec_off + (size_t)a.n_chains * *n_vecs * (size_t)(*G * *NP) * sizeof(double2);
   if ((size_t)c->machine_bytes < need) return LMC_ERR_WORKSPACE;

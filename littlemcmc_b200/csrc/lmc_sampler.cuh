@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
 
   const int D = a.ndim;
   const int ldh = (int)(a.ld >> 1);
-  const int tail = vid_tail(a.max_treedepth);
+  const int tail = vid_tail(scratch_depth(a));
 
   for (;;) {
     // ---- pop the next (chain, transition) unit ---------------------------------------------------------------------
@@ -464,7 +464,7 @@ int launch(const lmc_sampler_args& a, const Target& tgt) {
   LMC_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
 
   KernelCfg cfg;
-  cfg.ws_vecs = KIND == KIND_NUTS ? ws_vecs_nuts(a.max_treedepth) : 0;
+  cfg.ws_vecs = KIND == KIND_NUTS ? ws_vecs_nuts(scratch_depth(a)) : 0;
   const size_t red_bytes = (size_t)CPB * (2 * Group<G>::kWarps * kRedSlots * sizeof(double) + sizeof(StackScalars));
   const size_t vec_bytes = (size_t)VS * sizeof(double2);
   // shared-memory policy: give each CTA an equal share of the SM for the CTAs the register file can hold, and
@@ -477,7 +477,7 @@ int launch(const lmc_sampler_args& a, const Target& tgt) {
     const size_t per_cta = (size_t)(227 * 1024) / occ0 - 1024;  // 1 KB/CTA reserved by the driver
     const size_t cap = per_cta < (size_t)smem_optin ? per_cta : (size_t)smem_optin;
     n_smem = cap > red_bytes ? (int)((cap - red_bytes) / (CPB * vec_bytes)) : 0;
-    const int hot = vid_tail(a.max_treedepth);
+    const int hot = vid_tail(scratch_depth(a));
     if (n_smem > hot) n_smem = hot;
     if (a.tune_smem_vecs >= 0) n_smem = a.tune_smem_vecs < hot ? a.tune_smem_vecs : hot;
   }

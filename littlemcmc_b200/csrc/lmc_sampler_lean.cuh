@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(G, MINCTAS) sampler_lean_kernel(const lmc_samp
 
   const int D = a.ndim;
   const int ldh = (int)(a.ld >> 1);
-  const int tail = vid_tail(a.max_treedepth);
+  const int tail = vid_tail(scratch_depth(a));
 
   for (;;) {
     // ---- pop the next (chain, transition) unit (lmc_sampler.cuh: scheduler) -------------------------------------------
@@ -476,7 +476,7 @@ int launch_lean(const lmc_sampler_args& a, const Target& tgt) {
   LMC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   LMC_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   KernelCfg cfg;
-  cfg.ws_vecs = ws_vecs_nuts(a.max_treedepth);
+  cfg.ws_vecs = ws_vecs_nuts(scratch_depth(a));
   const size_t red_bytes = 2 * Group<G>::kWarps * kRedSlots * sizeof(double) + sizeof(StackScalars);
   const size_t vec_bytes = (size_t)VS * sizeof(double2);
   const size_t fixed = red_bytes + LS_COUNT * vec_bytes;
@@ -488,7 +488,7 @@ int launch_lean(const lmc_sampler_args& a, const Target& tgt) {
   const size_t per_cta = (size_t)(227 * 1024) / occ0 - 1024;
   const size_t cap = per_cta < (size_t)smem_optin ? per_cta : (size_t)smem_optin;
   int n_smem = cap > fixed ? (int)((cap - fixed) / vec_bytes) : 0;
-  const int hot = vid_tail(a.max_treedepth);
+  const int hot = vid_tail(scratch_depth(a));
   if (n_smem > hot) n_smem = hot;
   if (a.tune_smem_vecs >= 0) n_smem = a.tune_smem_vecs < hot ? a.tune_smem_vecs : hot;
   cfg.n_smem_vecs = n_smem;

@@ -37,6 +37,12 @@ __host__ __device__ constexpr int tvid(int tail, int t) {
   return t == T_PSUM ? 0 : t == T_LP ? 1 : t == T_RP ? 2 : tail + t;
 }
 __host__ __device__ constexpr int ws_vecs_nuts(int max_depth) { return vid_tail(max_depth) + T_COUNT; }
+// Depth the scratch is sized for.  Trees grow to early_max_treedepth while tune && iter_count < 200 (nuts.py:205-208),
+// and NUTS(max_treedepth=5) keeps the default early_max_treedepth=8 in the reference: both caps bound the stack.
+// The *_bytes entry points take this value as their `max_treedepth` argument.
+__host__ __device__ inline int scratch_depth(const lmc_sampler_args& a) {
+  return a.max_treedepth > a.early_max_treedepth ? a.max_treedepth : a.early_max_treedepth;
+}
 
 // per-level scalars of the subtree stack (written by lane 0 only; every read is separated from the write by a group
 // barrier / __syncwarp or by a kernel boundary)

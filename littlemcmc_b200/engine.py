@@ -12,9 +12,6 @@ import torch
 from . import _lib as L
 
 
-import os as _os
-_DIRECT_CB = _os.environ.get("LMC_DIRECT_CB", "1") == "1"     # experiment switch (callback output buffers, see CallbackRun)
-
 _GRAPH_RES = {}   # device -> (side stream, CUDA-graph memory pool) of callback mode
 
 # launches of this library's kernels enqueued by this process (bench.py reports the count inside its timed region)
@@ -187,7 +184,7 @@ def run_transitions(kind, chains, target, *, n_trans, iter0, n_tune, params, see
                           tapes=tapes, trace=trace, stats=stats, knobs=knobs, stream=stream,
                           step_size_override=step_size_override)
         a.target = target.c_struct(dev)
-        nbytes = lib.lmc_workspace_bytes(kind, Cn, D, a.max_treedepth, a.tune_group)
+        nbytes = lib.lmc_workspace_bytes(kind, Cn, D, max(a.max_treedepth, a.early_max_treedepth), a.tune_group)
         if nbytes < 0:
             L.check(int(nbytes), "lmc_workspace_bytes")
         ws = chains.workspace(nbytes)
@@ -250,14 +247,15 @@ class CallbackRun:
             self.keep = _fill_base(self.c.base, kind, chains, n_trans=n_trans, iter0=iter0, n_tune=n_tune, params=params,
                                    seeds=seeds, tapes=tapes, trace=self.trace, stats=self.stats, knobs=None, stream=stream,
                                    step_size_override=step_size_override)
-            nbytes = self.lib.lmc_callback_state_bytes(kind, Cn, D, self.c.base.max_treedepth)
+            nbytes = self.lib.lmc_callback_state_bytes(kind, Cn, D, max(self.c.base.max_treedepth,
+                                                                               self.c.base.early_max_treedepth))
             if nbytes < 0:
                 L.check(int(nbytes), "lmc_callback_state_bytes")
             self.machine = chains.workspace(nbytes)
         c = self.c
         c.q_eval, c.g_eval, c.logp_eval = self.q_eval.data_ptr(), self.g_eval.data_ptr(), self.logp_eval.data_ptr()
         c.machine, c.machine_bytes, c.n_running = self.machine.data_ptr(), self.machine.numel(), self.n_running.data_ptr()
-        per = (1 << c.base.max_treedepth) + 1 if kind == L.KIND_NUTS else c.base.max_steps + 1
+        per = (1 << max(c.base.max_treedepth, c.base.early_max_treedepth)) + 1 if kind == L.KIND_NUTS else c.base.max_steps + 1
         self.max_iters = int(n_trans) * per + 1
         self.n_evals = 0
 
@@ -276,13 +274,13 @@ class CallbackRun:
         c = self.c
         # hand the callback's own output buffers to the kernel when their layout allows it (rows of D = ld doubles,
         # 16-byte aligned): saves two copy kernels per gradient evaluation in this launch-latency-bound mode
-        if (_DIRECT_CB and D == self.chains.ld and grad.is_contiguous() and grad.dtype == torch.float64 and grad.data_ptr() % 16 == 0
+        if (D == self.chains.ld and grad.is_contiguous() and grad.dtype == torch.float64 and grad.data_ptr() % 16 == 0
                 and grad.device == self.q_eval.device):
             c.g_eval = grad.data_ptr()
         else:
             self.g_eval[:, :D].copy_(grad)
             c.g_eval = self.g_eval.data_ptr()
-        if _DIRECT_CB and logp.is_contiguous() and logp.dtype == torch.float64 and logp.device == self.q_eval.device:
+        if logp.is_contiguous() and logp.dtype == torch.float64 and logp.device == self.q_eval.device:
             c.logp_eval = logp.data_ptr()
         else:
             self.logp_eval.copy_(logp)
@@ -298,7 +296,7 @@ class CallbackRun:
         with torch.cuda.device(dev):
             self.begin()
             if iters_per_graph is None:
-                iters_per_graph = int(_os.environ.get("LMC_CB_GRAPH_ITERS", "8"))
+                iters_per_graph = 8
             if cuda_graph:
                 self._run_graphed(iters_per_graph)
             else:
@@ -386,7 +384,8 @@ class DenseRun:
                                    seeds=seeds, tapes=tapes, trace=self.trace, stats=self.stats, knobs=None, stream=stream,
                                    step_size_override=step_size_override)
             self.c.base.adapt_mass = int(bool(getattr(potential, "_adaptive", False)))
-            nbytes = self.lib.lmc_dense_state_bytes(kind, Cn, chains.ndim, self.c.base.max_treedepth)
+            nbytes = self.lib.lmc_dense_state_bytes(kind, Cn, chains.ndim, max(self.c.base.max_treedepth,
+                                                                                   self.c.base.early_max_treedepth))
             if nbytes < 0:
                 L.check(int(nbytes), "lmc_dense_state_bytes")
             self.machine = chains.workspace(nbytes)
@@ -395,7 +394,7 @@ class DenseRun:
         c.x_eval, c.v_eval = self.x_eval.data_ptr(), self.v_eval.data_ptr()
         c.n_eval, c.p0_eval, c.need = self.n_eval.data_ptr(), self.p0_eval.data_ptr(), self.need.data_ptr()
         c.machine, c.machine_bytes, c.n_running = self.machine.data_ptr(), self.machine.numel(), self.n_running.data_ptr()
-        per = (1 << c.base.max_treedepth) + 2 if kind == L.KIND_NUTS else c.base.max_steps + 2
+        per = (1 << max(c.base.max_treedepth, c.base.early_max_treedepth)) + 2 if kind == L.KIND_NUTS else c.base.max_steps + 2
         self.max_iters = 2 * int(n_trans) * per + 4
         self.n_grad_evals = self.n_vel_evals = 0
 

@@ -46,7 +46,7 @@ def _resolve_seeds(random_seed, chains):
 def sample(logp_dlogp_func, model_ndim, draws=1000, tune=1000, step=None, init="auto", chains=None, cores=None,
            start=None, progressbar=True, random_seed=None, discard_tuned_samples=True, chain_idx=0, callback=None,
            mp_ctx=None, pickle_backend="pickle", device=None, block=None, return_device=False, host_write="copy",
-           _timing=None, **kwargs):
+           stats_as="dict", _timing=None, **kwargs):
     """Draw samples with the given step method; signature and return value of reference `sample` (sampling.py:35-222).
 
     Returns ``(trace, stats)``: ``trace`` float64 ``[chains, draws, model_ndim]``; ``stats`` a dict of arrays
@@ -65,7 +65,8 @@ def sample(logp_dlogp_func, model_ndim, draws=1000, tune=1000, step=None, init="
     copied out by the copy engine on a side stream while the next block samples (measured: 66 ms for 3.3 GB of draws
     next to 54 ms of sampling); ``"direct"``: the sampler kernel stores each draw straight into the mapped pinned
     buffer (no staging; measured slower, 74 ms, because the stores back-pressure the sampling groups; fused targets
-    only).
+    only); ``stats_as="tensor"`` (with ``return_device``): the statistics as the ONE ``[chains, draws, 13]`` device
+    tensor the kernels write (columns = ``step._stat_columns``) instead of a dict of views of it.
     """
     import time as _time
     _t = [_time.perf_counter()]
@@ -163,7 +164,8 @@ def sample(logp_dlogp_func, model_ndim, draws=1000, tune=1000, step=None, init="
             if callback is not None:
                 compute.synchronize()
                 copy_stream.synchronize()
-                _per_draw_callbacks(callback, step, st, tr_view, host_trace, done, n, T, int(tune), keep_from)
+                _per_draw_callbacks(callback, step, st, tr_view, host_trace, done, n, T, int(tune), keep_from,
+                                    int(chain_idx))
             done += n
             blk += 1
     except KeyboardInterrupt:                              # sampling.py:470-478: return what has been sampled so far
@@ -192,6 +194,8 @@ def sample(logp_dlogp_func, model_ndim, draws=1000, tune=1000, step=None, init="
     _mark("account")
     stats_kept = stats_dev[:, keep_from:]
     if return_device:
+        if stats_as == "tensor":
+            return trace_out, stats_kept.contiguous()
         stats = {name: stats_kept[:, :, col].unsqueeze(-1) for name, col in step._stat_columns.items()}
         return trace_out, stats
     # statistics: transpose on the device to one contiguous [chains, draws] plane per statistic, one pinned copy, and
@@ -209,8 +213,9 @@ def sample(logp_dlogp_func, model_ndim, draws=1000, tune=1000, step=None, init="
     return host_trace.numpy(), stats
 
 
-def _per_draw_callbacks(callback, step, st_dev, tr_dev_or_host, host_trace, first, n, T, tune, keep_from):
-    """Call the reference-style hook once per (draw, chain) of a finished block (sampling.py:303-308)."""
+def _per_draw_callbacks(callback, step, st_dev, tr_dev_or_host, host_trace, first, n, T, tune, keep_from, chain_idx=0):
+    """Call the reference-style hook once per (draw, chain) of a finished block (sampling.py:303-308).  `Draw.chain`
+    counts from `chain_idx`, like the reference's `chain=i + chain_idx` (sampling.py:173)."""
     st = st_dev.cpu().numpy()
     pts = tr_dev_or_host.cpu().numpy() if tr_dev_or_host.is_cuda else tr_dev_or_host.numpy()
     trace_np = None if host_trace is None else host_trace.numpy()
@@ -219,7 +224,7 @@ def _per_draw_callbacks(callback, step, st_dev, tr_dev_or_host, host_trace, firs
         idx = first + j
         for c in range(st.shape[0]):
             sd = {name: np.asarray(st[c, j, step._stat_columns[name]]).astype(dt)[()] for name, dt in dtypes.items()}
-            callback(trace=trace_np, draw=Draw(c, idx == T - 1, idx, idx < tune, [sd], pts[c, j], None))
+            callback(trace=trace_np, draw=Draw(c + chain_idx, idx == T - 1, idx, idx < tune, [sd], pts[c, j], None))
 
 
 def init_nuts(logp_dlogp_func, model_ndim, init="auto", random_seed=None, **kwargs):

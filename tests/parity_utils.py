@@ -308,3 +308,88 @@ def parity_report(res: ParityResult):
                      ("adapt", res.gpu_adapt, res.cpu_adapt), ("welford", res.gpu_welford, res.cpu_welford)):
         lines.append("  %-18s max rel %.2e" % (nm, rel(a, b)))
     return "\n".join(lines)
+
+
+# ---- replay of chains sampled from a FULL-SIZE device run -------------------------------------------------------------------
+def oracle_sampler_from_state(f, D, q, var, wel, scal, *, iter_count, tune, **sampler_kw):
+    """An oracle Sampler whose potential / step-size state is the snapshot (`_snapshot` order) read back from the
+    device for one chain: the inverse of `_snapshot`, used to replay one transition of a chain picked out of a
+    full-size run."""
+    pot = orc.DiagPotential(D, var=np.ones(D), initial_mean=np.zeros(D), initial_weight=10.0, adapt=True)
+    pot.var = np.array(var, dtype="d")
+    pot.stds = np.sqrt(pot.var)
+    pot.inv_stds = 1.0 / pot.stds
+    pot.fg = orc.Welford(np.array(wel[0], dtype="d"), np.array(wel[1], dtype="d"), float(scal[5]))
+    pot.bg = orc.Welford(np.array(wel[2], dtype="d"), np.array(wel[3], dtype="d"), float(scal[6]))
+    pot.n_samples, pot.adaptation_window = int(scal[7]), int(scal[8])
+    smp = orc.Sampler(f, D, pot, kind="nuts", **sampler_kw)
+    sa = smp.step_adapt
+    sa.log_step, sa.log_bar, sa.hbar, sa.count, sa.mu = (float(scal[0]), float(scal[1]), float(scal[2]),
+                                                         int(scal[3]), float(scal[4]))
+    smp.tune, smp.iter_count = bool(tune), int(iter_count)
+    return smp
+
+
+def replay_sampled_chains(f, fused_target, D, n_chains, *, max_treedepth, n_warm, n_check, n_sample=8, seed=0,
+                          start=None, knobs=None, device="cuda:0"):
+    """Full-size run on the GPU with in-kernel Philox randomness and the FIFO scheduler under contention; after `n_warm`
+    tuning transitions, `n_check` more are launched one at a time and `n_sample` randomly chosen chains are replayed in
+    the CPU oracle from their device pre-state, with their own Philox streams dumped by lmc_rng_fill.
+    -> list of ParityResult (one per checked transition)."""
+    import torch
+    from littlemcmc_b200 import _lib as L
+    from littlemcmc_b200 import engine
+    rs = np.random.RandomState(seed)
+    ch = engine.DeviceChains(n_chains, D, device)
+    ch.reset_potential(np.ones(D), np.zeros(D), 10.0, 101)
+    ch.reset_step_adapt(0.25 / D ** 0.25)
+    ch.set_position(np.zeros(D) if start is None else start)
+    params = dict(adapt_mass=1, adapt_step_size=1, target_accept=0.8, gamma=0.05, k=0.75, t0=10, Emax=1000.0,
+                  max_treedepth=max_treedepth, early_max_treedepth=8)
+    seeds_np = rs.randint(2 ** 30, size=n_chains)
+    seeds = engine.seeds_tensor(seeds_np, device)
+    big = 10 ** 9
+    if n_warm:
+        engine.run_transitions(L.KIND_NUTS, ch, fused_target, n_trans=n_warm, iter0=0, n_tune=big, params=params,
+                               seeds=seeds, knobs=knobs)
+    sel = np.sort(rs.choice(n_chains, size=n_sample, replace=False))
+    sel_t = torch.as_tensor(sel, device=device)
+    u_stride = (1 << max_treedepth) + max_treedepth + 8
+
+    def read():
+        wel = torch.stack([ch.mean_fg[sel_t, :D], ch.rawvar_fg[sel_t, :D], ch.mean_bg[sel_t, :D],
+                           ch.rawvar_bg[sel_t, :D]], 1)
+        return (ch.q[sel_t, :D].cpu().numpy(), ch.var[sel_t, :D].cpu().numpy(), wel.cpu().numpy(),
+                ch.adapt[sel_t, :9].cpu().numpy())
+
+    out = []
+    for t in range(n_check):
+        it = n_warm + t
+        pre = read()
+        _, st = engine.run_transitions(L.KIND_NUTS, ch, fused_target, n_trans=1, iter0=it, n_tune=big, params=params,
+                                       seeds=seeds, knobs=knobs)
+        torch.cuda.synchronize()
+        post = read()
+        st = st[sel_t, 0].cpu().numpy()
+        normals, uniforms = engine.rng_fill(seeds[sel_t], D, it, 1, u_stride)
+        normals, uniforms = normals.cpu().numpy(), uniforms.cpu().numpy()
+        assert int(st[:, L.STAT_N_UNIFORMS].max()) <= u_stride
+        names = orc.NUTS_STAT_NAMES + ("reached_max_treedepth",)
+        cpu_stats = {n: np.zeros((n_sample, 1)) for n in names}
+        cpu_q, cpu_var, cpu_wel, cpu_ad, n_u = [], [], [], [], []
+        for j in range(n_sample):
+            smp = oracle_sampler_from_state(f, D, pre[0][j], pre[1][j], pre[2][j], pre[3][j], iter_count=it, tune=True,
+                                            max_treedepth=max_treedepth, early_max_treedepth=8)
+            rng = orc.TapeRNG(normals[j], uniforms[j])
+            q, sd = smp.astep(pre[0][j], rng)
+            snap = _snapshot(smp, q)
+            cpu_q.append(snap[0]); cpu_var.append(snap[1]); cpu_wel.append(snap[2]); cpu_ad.append(snap[3])  # noqa: E702
+            n_u.append(rng._k)
+            for n in names:
+                cpu_stats[n][j, 0] = sd[n]
+        out.append(ParityResult(
+            "nuts", post[0][:, None], np.stack(cpu_q)[:, None], {n: st[:, i:i + 1] for n, i in NUTS_STATS.items()},
+            cpu_stats, post[1][:, None], np.stack(cpu_var)[:, None], post[3][:, None], np.stack(cpu_ad)[:, None],
+            post[2][:, None], np.stack(cpu_wel)[:, None], st[:, L.STAT_N_UNIFORMS][:, None],
+            np.array(n_u, dtype="d")[:, None], ch.status[sel_t].cpu().numpy()))
+    return out

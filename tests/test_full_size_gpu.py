@@ -111,7 +111,8 @@ def test_cfg2_1024x100_torch_logp_matches_fused_statistics():
     tgt = lmc.targets.DiagGaussian(sigma=sigma)
     _, t_f, s_f = _run(tgt, D, C, tune=60, draws=20, seed=2)
     _, t_c, s_c = _run(tgt.torch_batched("cuda:0", cuda_graph=True), D, C, tune=60, draws=20, seed=2)
-    assert torch.equal(s_f["tree_size"][:, 0], s_c["tree_size"][:, 0]) or True   # (tune rows are discarded)
+    # the first kept draw (transition 60) comes after 60 chained adaptive transitions: trajectories of the two modes
+    # have drifted apart by then (logp summation order), so the statistics are compared in distribution only
     assert abs(float(s_f["tree_size"].mean()) / float(s_c["tree_size"].mean()) - 1) < 0.1
     np.testing.assert_allclose(t_c.cpu().numpy().std((0, 1)), sigma, rtol=0.1)
     np.testing.assert_allclose(t_f.cpu().numpy().std((0, 1)), sigma, rtol=0.1)

@@ -80,6 +80,25 @@ def test_d1000_shapes(group):
     pu.assert_parity(res, rtol=RTOL)
 
 
+def test_fixtures_reach_the_depths_the_baseline_configs_run():
+    """BASELINE configs run max_treedepth 10 and 12: the committed reference fixtures must reach those depths (stack
+    levels 8..11, proposal slots 9..12, the all-global part of the scratch), and one must have tuning trees deeper
+    than max_treedepth (early_max_treedepth > max_treedepth, legal in the reference: nuts.py:205-208)."""
+    depth = {n: gc.load(n)[1]["stat_depth"].max() for n in gc.CASE_NAMES if n.startswith("nuts")}
+    assert depth["nuts_deep_d1000"] == 12 and depth["nuts_deep_funnel_d50"] == 12 and depth["nuts_deep_d100"] == 10
+    case, ref = gc.load("nuts_early_gt_max_d20")
+    assert int(case["max_treedepth"]) == 5 and ref["stat_depth"][:, :int(case["tune"])].max() == 8
+
+
+@pytest.mark.parametrize("smem", [-1, 0, 3])
+@pytest.mark.parametrize("group", [0, 32, 64, 256])
+def test_deep_trees_every_scratch_placement(group, smem):
+    """Depth-10 trees at D=100 through one warp per chain, a CTA per chain, with the scratch in shared memory (as much
+    as fits), all-global, and split after three vectors."""
+    res = pu.run_case_on_gpu_and_oracle("nuts_deep_d100", knobs=dict(group=group, smem_vecs=smem))
+    pu.assert_parity(res, rtol=RTOL)
+
+
 @pytest.mark.parametrize("callback", [None, "torch"])
 def test_reached_max_treedepth_flag(callback):
     """The for/else of nuts.py:212-220 (tree loop exhausted without divergence or U-turn, what
@@ -107,7 +126,8 @@ def test_step_rand_hook(callback):
 
 
 @pytest.mark.parametrize("group", [-64, -128])
-@pytest.mark.parametrize("name", ["nuts_illcond_d1000", "nuts_diag_d37", "nuts_static_d100", "nuts_funnel_d10", "nuts_b1_d10"])
+@pytest.mark.parametrize("name", ["nuts_illcond_d1000", "nuts_diag_d37", "nuts_static_d100", "nuts_funnel_d10", "nuts_b1_d10",
+                                  "nuts_deep_d1000", "nuts_deep_funnel_d50", "nuts_early_gt_max_d20"])
 def test_lean_kernel_parity(name, group):
     """The lean NUTS kernel (lmc_sampler_lean.cuh: only q, p, grad in registers; selected with a negative group knob)
     against the oracle, transition level, with its scratch in shared memory and all-global."""
