@@ -157,12 +157,13 @@ typedef struct lmc_sampler_args {
   void* workspace;     /* >= lmc_workspace_bytes(...) bytes, 16-byte aligned                                */
   int64_t workspace_bytes;
   void* stream;        /* cudaStream_t                                                                      */
-  int32_t tune_group;  /* 0 = library picks threads-per-chain; > 0: force 32/64/128/256/512/1024 with the
+  int32_t tune_group;  /* 0 = library picks the kernel and threads-per-chain; 1: force the chunked warp-per-chain
+                          NUTS kernel (ndim <= 256); >= 32: force 32/64/128/256/512/1024 threads per chain with the
                           register-resident kernel; < 0: force -tune_group (64/128/256) with the lean NUTS kernel
                           (experiments and tests)                                                            */
   int32_t tune_smem_vecs; /* -1 = library picks how many scratch vectors live in shared memory; else force  */
   int32_t tune_max_slots; /* 0 = library picks the number of resident chain slots; else cap it              */
-  int32_t reserved3;
+  int32_t tune_chunk;  /* chunked warp kernel: leaves per chunk (2, 4, 8, 16); 0 = library picks            */
 } lmc_sampler_args;
 
 /* Library / ABI version (LMC_ABI_VERSION of the build). */

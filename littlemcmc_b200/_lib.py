@@ -49,7 +49,7 @@ class SamplerArgs(C.Structure):
         ("stats", C.c_void_p), ("status", C.c_void_p), ("step_size_override", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("stream", C.c_void_p),
         ("tune_group", C.c_int32), ("tune_smem_vecs", C.c_int32), ("tune_max_slots", C.c_int32),
-        ("reserved3", C.c_int32),
+        ("tune_chunk", C.c_int32),
     ]
 
 

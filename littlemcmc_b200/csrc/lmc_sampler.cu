@@ -24,6 +24,8 @@ static int check_args(const lmc_sampler_args* a, int kind) {
     return LMC_ERR_BADARG;
   }
   if (kind == KIND_NUTS) {
+    if (a->tune_chunk != 0 && a->tune_chunk != 2 && a->tune_chunk != 4 && a->tune_chunk != 8 && a->tune_chunk != 16)
+      return LMC_ERR_BADARG;
     if (a->max_treedepth < 1 || a->max_treedepth > kMaxDepth) return LMC_ERR_UNSUPPORTED;
     if (a->early_max_treedepth < 0 || a->early_max_treedepth > kMaxDepth) return LMC_ERR_UNSUPPORTED;
   } else {
@@ -48,6 +50,13 @@ int run_funnel_hmc(const lmc_sampler_args& a, const Funnel& t);
 int run_gauss_nuts_lean(const lmc_sampler_args& a, const DiagGaussian& t, int group);
 int run_funnel_nuts_lean(const lmc_sampler_args& a, const Funnel& t, int group);
 bool pick_lean_shape(int ndim, int group, int* G, int* NP);
+// chunked warp-per-chain NUTS kernel (lmc_sampler_warp.cuh): the default up to 256 dimensions (tune_group 0), forced
+// with tune_group == 1
+int run_gauss_nuts_warp(const lmc_sampler_args& a, const DiagGaussian& t);
+int run_funnel_nuts_warp(const lmc_sampler_args& a, const Funnel& t);
+static bool use_warp_kernel(int kind, int ndim, int tune_group) {
+  return kind == KIND_NUTS && (ndim + 1) / 2 <= 128 && (tune_group == 0 || tune_group == 1);
+}
 static int lean_group(const lmc_sampler_args* a, int kind) {
   if (kind != KIND_NUTS) return 0;
   if (a->tune_group < 0) return -a->tune_group;
@@ -61,10 +70,12 @@ static int sample_entry(const lmc_sampler_args* a, int kind) {
   if (a->n_chains == 0 || a->n_trans == 0) return LMC_OK;
   if (a->target.kind == LMC_TARGET_DIAG_GAUSSIAN) {
     DiagGaussian t{reinterpret_cast<const double2*>(a->target.tau)};
+    if (use_warp_kernel(kind, a->ndim, a->tune_group)) return run_gauss_nuts_warp(*a, t);
     if (lean_group(a, kind)) return run_gauss_nuts_lean(*a, t, lean_group(a, kind));
     return kind == KIND_NUTS ? run_gauss_nuts(*a, t) : run_gauss_hmc(*a, t);
   }
   Funnel t{1.0 / (a->target.v_scale * a->target.v_scale), 0.5 * (double)(a->ndim - 1)};
+  if (use_warp_kernel(kind, a->ndim, a->tune_group)) return run_funnel_nuts_warp(*a, t);
   if (lean_group(a, kind)) return run_funnel_nuts_lean(*a, t, lean_group(a, kind));
   return kind == KIND_NUTS ? run_funnel_nuts(*a, t) : run_funnel_hmc(*a, t);
 }
@@ -77,6 +88,17 @@ extern "C" int64_t lmc_workspace_bytes(int32_t kind, int32_t n_chains, int32_t n
   if (kind == lmc::KIND_HMC) return (int64_t)lmc::sched_bytes(n_chains);
   if (kind != lmc::KIND_NUTS || max_treedepth < 1 || max_treedepth > lmc::kMaxDepth) return LMC_ERR_UNSUPPORTED;
   lmc::Shape s;
+  if (lmc::use_warp_kernel(kind, ndim, tune_group)) {
+    // one warp per slot, at most 32 one-warp CTAs per SM; scratch = tree stack + trajectory + the largest position ring
+    int dev = 0, n_sm = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    (void)cudaGetLastError();
+    const int np = (ndim + 1) / 2 <= 32 ? 1 : (ndim + 1) / 2 <= 64 ? 2 : 4;
+    long long slots = (long long)n_sm * 32;
+    if (slots > n_chains) slots = n_chains < 1 ? 1 : n_chains;
+    return (long long)lmc::sched_bytes(n_chains) +
+           slots * (lmc::ws_vecs_nuts(max_treedepth) + 16) * (long long)(32 * np) * (long long)sizeof(double2);
+  }
   if (tune_group < 0) {
     if (!lmc::pick_lean_shape(ndim, -tune_group, &s.G, &s.NP)) return LMC_ERR_UNSUPPORTED;
   } else if (!lmc::pick_shape(ndim, tune_group, &s)) {

@@ -1,0 +1,640 @@
+// Chunked warp-per-chain NUTS kernel: the sampler for small dimensions (ndim <= 256; BASELINE configs 2 and 4).
+//
+// Why a second kernel.  With one warp per chain the round-1 kernel (lmc_sampler.cuh) executed ~1300 instructions and
+// two dependent warp reductions per leapfrog, at ~19 cycles per instruction: every leaf is a chain of
+// leapfrog -> butterfly -> exp -> merge -> butterfly -> branchy bookkeeping, and with 1024 chains there are fewer than
+// two warps per scheduler to hide any of it (profiles/r02a_cfg2_ncu_full.md: 13% issue slots, 0.06 of roofline).
+//
+// What is different.  Inside one subtree the leapfrog TRAJECTORY does not depend on any tree decision (decisions only
+// pick proposals and stop early), so the tree is built in CHUNKS of B = 2^b consecutive leaves:
+//   1. B leapfrogs back to back, state in registers, NO reduction in between (targets whose gradient needs a sum,
+//      Target::kPre > 0, keep that one); every leaf's momentum goes to a shared-memory ring, its position to a global
+//      ring, and the per-lane partial sums of its kinetic energy / log density to a shared-memory table;
+//   2. all dot products of all B-1 merges INSIDE the chunk (levels 0 .. b-1 of reference nuts.py:387-398) are formed
+//      from the ring, every lane on its own columns, partials into the same table;
+//   3. ONE transposed reduction: lane r sums row r of the table (no shuffles), energies -> exp() on B lanes in
+//      parallel, U-turn flags -> one ballot;
+//   4. one scalar pass over the chunk in the reference's post-order (uniform across the warp, same uniforms in the same
+//      order as the recursion, stops at the first divergence / turn: leaves after it are discarded, and were the only
+//      wasted work);
+//   5. the chunk's subtree (level b) is merged with the stack levels >= b exactly as before (lmc_tree.cuh merge_level,
+//      vectors in the L2-resident workspace: touched once per B leaves).
+// Same arithmetic per element and the same decisions as the reference; dot products are summed in a fixed but
+// different order than the butterfly (like BLAS ddot, unspecified), so results agree with the oracle to the same
+// ~1e-13 as the other kernels.  Shared memory per resident chain: B * NP * 512 B of momentum ring + table.
+#pragma once
+#include "lmc_sampler.cuh"
+
+namespace lmc {
+
+struct WarpCfg {
+  int slot_bytes;  // shared memory per warp slot
+  int ws_vecs;     // global scratch vectors per slot (tree stack + trajectory + position ring)
+  int n_smem_vecs; // tree-scratch vectors kept in shared memory (ids < n_smem_vecs)
+};
+
+template <int NP, int B>
+struct WarpLayout {
+  static constexpr int VS = 32 * NP;                 // pairs per vector
+  static constexpr int kRows = 6 * B - 6;            // table rows: 2B energy partials + (4B - 6) merge dot products
+  static constexpr int kLog = (B == 2 ? 1 : B == 4 ? 2 : B == 8 ? 3 : 4);
+  static_assert(B == 2 || B == 4 || B == 8 || B == 16, "chunk of 2, 4, 8 or 16 leaves");
+  // byte offsets inside a slot
+  static constexpr int oRingP = 0;
+  static constexpr int oPs = oRingP + B * VS * 16;
+  static constexpr int oVar = oPs + (B / 2) * VS * 16;
+  static constexpr int oPart = oVar + VS * 16;
+  static constexpr int oVal = oPart + kRows * 32 * 8;
+  // val: E[B], logp[B], dE[B], wm[B], pre[2B], dot[4B-6 (+pad)], local stack (kLog + 1) x 5 doubles, we[B] ints, lpidx ints
+  static constexpr int nValD = 6 * B + (4 * B - 6 + 2) + 5 * (kLog + 1);
+  static constexpr int oInts = oVal + nValD * 8;
+  static constexpr int nInts = B + 3 * (kLog + 1) + 1;
+  static constexpr int oSS = ((oInts + nInts * 4) + 15) & ~15;
+  static constexpr int kFixedBytes = ((oSS + (int)sizeof(StackScalars)) + 15) & ~15;  // scratch vectors follow
+};
+
+template <class Target, int NP, int B, int WPB, int MINB>
+__global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_sampler_args a, const Target tgt,
+                                                                      const WarpCfg cfg) {
+  using LY = WarpLayout<NP, B>;
+  constexpr int G = 32;
+  constexpr int VS = LY::VS;
+  constexpr unsigned FULL = 0xffffffffu;
+  extern __shared__ double2 smem2[];
+  const int wib = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int slot = blockIdx.x * WPB + wib;
+  char* const base = reinterpret_cast<char*>(smem2) + (size_t)wib * cfg.slot_bytes;
+  double2* const ring_p = reinterpret_cast<double2*>(base + LY::oRingP) + lane;  // [B][NP][32]
+  double2* const psbuf = reinterpret_cast<double2*>(base + LY::oPs) + lane;     // [B/2][NP][32]
+  double2* const s_var = reinterpret_cast<double2*>(base + LY::oVar) + lane;    // [NP][32]
+  double* const part = reinterpret_cast<double*>(base + LY::oPart);             // [kRows][32], column skewed by row
+  double* const vE = reinterpret_cast<double*>(base + LY::oVal);
+  double* const vLogp = vE + B;
+  double* const vdE = vLogp + B;
+  double* const vWm = vdE + B;
+  double* const vPre = vWm + B;        // [B][2]
+  double* const vDot = vPre + 2 * B;   // [4B - 6]
+  double* const lstk = vDot + (4 * B - 6 + 2);  // local stack: [kLog + 1][5] = wm, am, pE, plogp, (unused)
+  int* const vWe = reinterpret_cast<int*>(base + LY::oInts);  // [B]
+  int* const lstk_i = vWe + B;                                // [kLog + 1][3] = we, ae, pidx
+  StackScalars* const ss = reinterpret_cast<StackScalars*>(base + LY::oSS);
+  Scratch<G, NP> sc;
+  sc.sm = reinterpret_cast<double2*>(base + LY::kFixedBytes);
+  sc.ws = reinterpret_cast<double2*>(reinterpret_cast<char*>(a.workspace) + sched_bytes(a.n_chains)) +
+          (size_t)slot * cfg.ws_vecs * VS;
+  sc.n_smem = cfg.n_smem_vecs;
+  sc.lane = lane;
+  Group<G> grp(lane, nullptr);
+  const SchedView sv = sched_view(a.workspace, a.n_chains);
+  const unsigned total_units = (unsigned)a.n_chains * (unsigned)a.n_trans;
+
+  const int D = a.ndim;
+  const int ldh = (int)(a.ld >> 1);
+  const int sdepth = scratch_depth(a);
+  const int tail = vid_tail(sdepth);
+  // position ring of the current chunk: B vectors after the tree scratch of this slot (global, written once per leaf,
+  // read back only for the one position per chunk that survives as a proposal)
+  double2* const ring_q = sc.ws + (size_t)ws_vecs_nuts(sdepth) * VS + lane;
+  auto skew = [&](int row) -> double* { return part + row * 32 + ((lane + row) & 31); };
+  // sum of table row `row` over the 32 lanes' partials (fixed order: physical columns row, row+1, ..)
+  auto row_sum = [&](int row) -> double {
+    const double* r = part + row * 32;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 32; k += 4) {
+      s0 += r[(k + 0 + row) & 31];
+      s1 += r[(k + 1 + row) & 31];
+      s2 += r[(k + 2 + row) & 31];
+      s3 += r[(k + 3 + row) & 31];
+    }
+    return (s0 + s1) + (s2 + s3);
+  };
+
+  for (;;) {
+    // ---- pop the next (chain, transition) unit (lmc_sampler.cuh: scheduler) ---------------------------------------------
+    int chain = -1, t = 0;
+    if (lane == 0) {
+      const unsigned h = atomicAdd(&sv.ctr[0], 1u);
+      if (h < total_units) {
+        volatile unsigned long long* e = sv.ring + (h % (unsigned)a.n_chains);
+        unsigned long long v = *e;
+        while ((unsigned)(v >> 32) != h + 1u) {
+          __nanosleep(200);
+          v = *e;
+        }
+        __threadfence();
+        chain = (int)(unsigned)v;
+        t = *(volatile int*)(sv.prog + (chain & 0x7fffffff));
+      }
+    }
+    chain = __shfl_sync(FULL, chain, 0);
+    t = __shfl_sync(FULL, t, 0);
+    if (chain == -1) break;
+    bool dead = ((unsigned)chain & kDeadBit) != 0u;
+    chain &= 0x7fffffff;
+    const size_t row = (size_t)chain * a.n_trans + t;
+    auto stats_row = [&]() -> double* { return a.stats + row * LMC_NSTATS; };
+    auto trace_row = [&]() -> double* {
+      return a.trace + (size_t)chain * a.trace_chain_stride + (size_t)t * a.trace_draw_stride;
+    };
+    int status = 0;
+
+    if (!dead) {
+      double2 q[NP], p[NP], g[NP];
+      load_row_cg<G, NP>(a.q + (size_t)chain * a.ld, lane, ldh, q);
+      mask_tail<G, NP>(lane, D, q);
+      {
+        double2 var[NP];
+        load_row_cg<G, NP>(a.var + (size_t)chain * a.ld, lane, ldh, var);
+        mask_tail<G, NP>(lane, D, var);
+#pragma unroll
+        for (int k = 0; k < NP; ++k) s_var[k * 32] = var[k];
+      }
+      const uint64_t seed = (a.rng.mode == LMC_RNG_PHILOX) ? a.rng.seeds[chain] : 0ull;
+      const long long it = a.iter0 + t;
+      const bool tune = it < a.n_tune;
+      const bool adapt_step = tune && a.adapt_step_size;
+      unsigned uc = 0;
+      double u_lane = 0.0;
+      auto next_uniform = [&]() -> double {
+        double u;
+        if (a.rng.mode == LMC_RNG_TAPE) {
+          if ((long long)uc < a.rng.u_stride) {
+            u = a.rng.uniforms[row * a.rng.u_stride + uc];
+          } else {
+            u = 0.5;
+            status |= LMC_STATUS_TAPE_EXHAUSTED;
+          }
+        } else {
+          if ((uc & 31u) == 0u) u_lane = philox_uniform(seed, it, uc + (unsigned)lane);
+          u = __shfl_sync(FULL, u_lane, (int)(uc & 31u));
+        }
+        ++uc;
+        return u;
+      };
+
+      // ---- p0 = potential.random()  (quadpotential.py:221-224 / 374-376) ------------------------------------------
+      {
+        const double* normals_row = a.rng.mode == LMC_RNG_TAPE ? a.rng.normals + row * D : nullptr;
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+          const int j = lane + k * G;
+          double2 n = make_double2(0.0, 0.0);
+          if (normals_row) {
+            if (2 * j < D) n.x = normals_row[2 * j];
+            if (2 * j + 1 < D) n.y = normals_row[2 * j + 1];
+          } else if (2 * j < D) {
+            n = philox_normal_pair(seed, it, (uint32_t)j);
+          }
+          const double2 vk = s_var[k * 32];
+          p[k].x = (2 * j < D) ? mul_rn(inv_sqrt_cold(vk.x), n.x) : 0.0;
+          p[k].y = (2 * j + 1 < D) ? mul_rn(inv_sqrt_cold(vk.y), n.y) : 0.0;
+        }
+      }
+
+      // ---- start = integrator.compute_state(q0, p0)  (integration.py:52-66) ----------------------------------------
+      double E0, logp0;
+      {
+        double pre[2] = {0.0, 0.0};
+        if constexpr (Target::kPre > 0) {
+          tgt.template pre<G, NP>(lane, D, q, pre);
+          grp.allreduce(pre);
+        }
+        double acc[2];
+        acc[1] = tgt.template grad<G, NP>(lane, D, ldh, q, g, pre);
+        acc[0] = 0.0;
+#pragma unroll
+        for (int k = 0; k < NP; ++k) acc[0] = dot2(acc[0], p[k], mul2(s_var[k * 32], p[k]));
+        grp.allreduce(acc);
+        logp0 = tgt.finish(acc[1], pre);
+        E0 = 0.5 * acc[0] - logp0;
+      }
+      if (!isfinite(E0)) {
+        status |= LMC_STATUS_BAD_INITIAL_ENERGY;
+        dead = true;
+      } else {
+        double eps = exp_cold(__ldcg(a.adapt + (size_t)chain * LMC_ADAPT_STRIDE +
+                                     (adapt_step ? LMC_ADAPT_LOG_STEP : LMC_ADAPT_LOG_BAR)));
+        if (a.step_size_override) eps = __ldg(a.step_size_override + chain);
+        bool diverging = false, reached_max = false;
+        const int max_depth = (tune && it < 200) ? a.early_max_treedepth : a.max_treedepth;  // nuts.py:205-208
+        TrajScalars tr{xf_zero(), xf_zero(), 0.0, E0, logp0, 0, 0};
+        int reg_edge = 0;
+        tree_init<G, NP>(sc, tail, q, p, g);
+        reached_max = max_depth <= 0;
+        for (int d = 0; d < max_depth; ++d) {  // nuts.py:212
+          const int dir = (next_uniform() < 0.5) ? 1 : -1;
+          if (reg_edge != 0 && reg_edge != dir) {
+            const int eb = (dir > 0 ? T_RQ : T_LQ);
+#pragma unroll
+            for (int k = 0; k < NP; ++k) {
+              q[k] = sc.vec(tvid(tail, eb + 0))[k * G];
+              p[k] = sc.vec(tvid(tail, eb + 1))[k * G];
+              g[k] = sc.vec(tvid(tail, eb + 2))[k * G];
+            }
+          }
+          const double eps_d = dir > 0 ? eps : -eps;
+          const double dt = 0.5 * eps_d;
+          unsigned free_slots = 0xffffffffu;  // pool of proposal slots of the stack levels >= b
+          int fail = 0;                       // 1 = diverging, 2 = turning
+          long long n_leaves = 0;
+          const unsigned n_leaf_total = 1u << d;
+          const int Bc = n_leaf_total < (unsigned)B ? (int)n_leaf_total : B;  // leaves per chunk
+          const int bc = 31 - __clz(Bc);                                     // its level
+          const unsigned n_chunks = n_leaf_total / (unsigned)Bc;
+          CurTree cur{xf_zero(), xf_zero(), 0.0, 0.0, kLeafProp};
+          int pidx = 0;  // ring index of cur's proposal while cur.pslot == kLeafProp ("still in the position ring")
+
+          for (unsigned c = 0; c < n_chunks && !fail; ++c) {
+            // ---- 1. Bc leapfrogs (integration.py:100-121), no reduction between them ------------------------------------
+            for (int s = 0; s < Bc; ++s) {
+              double pre[2] = {0.0, 0.0};
+#pragma unroll
+              for (int k = 0; k < NP; ++k) {
+                p[k] = axpy2(p[k], dt, g[k]);
+                q[k] = axpy2(q[k], eps_d, mul2(s_var[k * 32], p[k]));
+              }
+              if constexpr (Target::kPre > 0) {
+                tgt.template pre<G, NP>(lane, D, q, pre);
+                grp.allreduce(pre);
+                if (lane == 0) {
+                  vPre[2 * s] = pre[0];
+                  vPre[2 * s + 1] = pre[1];
+                }
+              }
+              const double lp_part = tgt.template grad<G, NP>(lane, D, ldh, q, g, pre);
+              double k_part = 0.0;
+#pragma unroll
+              for (int k = 0; k < NP; ++k) {
+                p[k] = axpy2(p[k], dt, g[k]);
+                k_part = dot2(k_part, p[k], mul2(s_var[k * 32], p[k]));
+                ring_p[(s * NP + k) * 32] = p[k];
+                ring_q[(size_t)(s * NP + k) * 32] = q[k];
+              }
+              *skew(s) = k_part;
+              *skew(B + s) = lp_part;
+            }
+            // ---- 2. dot products of the merges inside the chunk (nuts.py:387-398), every lane on its own columns ------------
+            if (Bc >= 2) {
+              for (int k2 = 0; k2 < Bc / 2; ++k2) {  // level 0: two leaves
+                double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+                for (int k = 0; k < NP; ++k) {
+                  const double2 pa = ring_p[((2 * k2) * NP + k) * 32], pb = ring_p[((2 * k2 + 1) * NP + k) * 32];
+                  const double2 vk = s_var[k * 32];
+                  const double2 ps = add2(pa, pb);          // p_sum = tree1.p_sum + tree2.p_sum (:390)
+                  d0 = dot2(d0, ps, mul2(vk, pa));          // p_sum . left.v
+                  d1 = dot2(d1, ps, mul2(vk, pb));          // p_sum . right.v
+                  psbuf[(k2 * NP + k) * 32] = ps;
+                }
+                *skew(2 * B + 2 * k2) = d0;
+                *skew(2 * B + 2 * k2 + 1) = d1;
+              }
+              int row0 = 2 * B + Bc;
+              for (int l = 1; (2 << l) <= Bc; ++l) {  // level l: two subtrees of `span` leaves each
+                const int span = 1 << l;
+                const int n_m = Bc / (2 * span);
+                for (int k2 = 0; k2 < n_m; ++k2) {
+                  const int first = k2 * 2 * span;
+                  double d6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                  for (int k = 0; k < NP; ++k) {
+                    const double2 t1_lp = ring_p[((first)*NP + k) * 32], t1_rp = ring_p[((first + span - 1) * NP + k) * 32];
+                    const double2 t2_lp = ring_p[((first + span) * NP + k) * 32];
+                    const double2 t2_rp = ring_p[((first + 2 * span - 1) * NP + k) * 32];
+                    const double2 t1_ps = psbuf[((2 * k2) * NP + k) * 32], t2_ps = psbuf[((2 * k2 + 1) * NP + k) * 32];
+                    const double2 vk = s_var[k * 32];
+                    const double2 ps = add2(t1_ps, t2_ps);   // :390
+                    const double2 ps1 = add2(t1_ps, t2_lp);  // tree1.p_sum + tree2.left.p (:394)
+                    const double2 ps2 = add2(t1_rp, t2_ps);  // tree1.right.p + tree2.p_sum (:396)
+                    const double2 v1l = mul2(vk, t1_lp), v1r = mul2(vk, t1_rp);
+                    const double2 v2l = mul2(vk, t2_lp), v2r = mul2(vk, t2_rp);
+                    d6[0] = dot2(d6[0], ps, v1l);
+                    d6[1] = dot2(d6[1], ps, v2r);
+                    d6[2] = dot2(d6[2], ps1, v1l);
+                    d6[3] = dot2(d6[3], ps1, v2l);
+                    d6[4] = dot2(d6[4], ps2, v1r);
+                    d6[5] = dot2(d6[5], ps2, v2r);
+                    psbuf[(k2 * NP + k) * 32] = ps;  // in place: entries 2 k2, 2 k2 + 1 >= k2 are not read again
+                  }
+#pragma unroll
+                  for (int e = 0; e < 6; ++e) *skew(row0 + 6 * k2 + e) = d6[e];
+                }
+                row0 += 6 * n_m;
+              }
+            }
+            __syncwarp();
+            // ---- 3. one transposed reduction: lane r sums row r ---------------------------------------------------------------
+            {
+              // energies: rows s (kinetic) and B + s (log-density sums), s < Bc
+              double sum = 0.0;
+              if (lane < Bc || (lane >= B && lane < B + Bc)) sum = row_sum(lane);
+              const double lp_s = __shfl_sync(FULL, sum, (lane + B) & 31);
+              if (lane < Bc) {
+                double pre[2] = {0.0, 0.0};
+                if constexpr (Target::kPre > 0) {
+                  pre[0] = vPre[2 * lane];
+                  pre[1] = vPre[2 * lane + 1];
+                }
+                const double logp = tgt.finish(lp_s, pre);
+                const double E = 0.5 * sum - logp;
+                double dE = E - E0;                       // nuts.py:352
+                if (isnan(dE)) dE = CUDART_INF;           // :353-354
+                XF w = xf_zero();
+                if (fabs(dE) < a.Emax) w = xf_exp(-dE);   // log_size = -dE (:359)
+                vE[lane] = E;
+                vLogp[lane] = logp;
+                vdE[lane] = dE;
+                vWm[lane] = w.m;
+                vWe[lane] = w.e;
+              }
+              // merge dot products: rows 2B .. 2B + 4 Bc - 7
+              const int n_dot = Bc >= 2 ? 4 * Bc - 6 : 0;
+              for (int r = lane; r < n_dot; r += 32) vDot[r] = row_sum(2 * B + r);
+            }
+            __syncwarp();
+            // U-turn flags of the chunk's merges, one lane per merge: id = (Bc - (Bc >> l)) + k2 for level l
+            unsigned turnmask = 0u;
+            if (Bc >= 2) {
+              bool flag = false;
+              if (lane < Bc - 1) {
+                int l = 0, idx = lane, cnt = Bc / 2;
+                while (idx >= cnt) {
+                  idx -= cnt;
+                  cnt >>= 1;
+                  ++l;
+                }
+                if (l == 0) {
+                  flag = (vDot[2 * idx] <= 0) || (vDot[2 * idx + 1] <= 0);  // :391
+                } else {
+                  // first row of level l: Bc + 6 * (Bc/4 + .. + Bc/2^l) = Bc + 6 * (Bc/2 - (Bc >> (l + 1))) ... per level sizes
+                  int r0 = Bc;
+                  for (int ll = 1; ll < l; ++ll) r0 += 6 * (Bc >> (ll + 1));
+                  const double* dd = vDot + r0 + 6 * idx;
+                  flag = (dd[0] <= 0) || (dd[1] <= 0) || (dd[2] <= 0) || (dd[3] <= 0) || (dd[4] <= 0) || (dd[5] <= 0);  // :391-398
+                }
+              }
+              turnmask = __ballot_sync(FULL, flag);
+            }
+            // ---- 4. the chunk's leaves and merges in the reference's post-order (uniform across the warp) -------------------
+            for (int s = 0; s < Bc; ++s) {
+              ++n_leaves;
+              const double dE = vdE[s];
+              if (fabs(dE) > fabs(tr.max_dE)) tr.max_dE = dE;  // :356-357
+              if (!(fabs(dE) < a.Emax)) {                      // :358 / :370-375
+                fail = 1;
+                break;
+              }
+              cur.w = XF{vWm[s], vWe[s]};
+              cur.a = (-dE < 0.0) ? xf_sqr(cur.w) : cur.w;     // log_p_accept_weighted = -dE + min(0, -dE)  (:363)
+              cur.pE = vE[s];
+              cur.plogp = vLogp[s];
+              cur.pslot = kLeafProp;
+              pidx = s;
+              int lvl = 0;
+              for (int bits = s; bits & 1; bits >>= 1, ++lvl) {
+                const int mid = (Bc - (Bc >> lvl)) + (s >> (lvl + 1));
+                const double u = next_uniform();
+                const double* ls = lstk + 5 * lvl;
+                const XF t1w{ls[0], lstk_i[3 * lvl]}, t1a{ls[1], lstk_i[3 * lvl + 1]};
+                const XF nw = xf_add(t1w, cur.w);   // log_size = logaddexp(...)            (:400)
+                const XF na = xf_add(t1a, cur.a);   // log_weighted_accept_sum              (:401-403)
+                if (!xf_u_less(u, nw, cur.w)) {     // logbern(tree2.log_size - log_size)   (:404): keep tree1's proposal
+                  cur.pE = ls[2];
+                  cur.plogp = ls[3];
+                  pidx = lstk_i[3 * lvl + 2];
+                }
+                cur.w = nw;
+                cur.a = na;
+                if ((turnmask >> mid) & 1u) {
+                  fail = 2;
+                  break;
+                }
+              }
+              if (fail) break;
+              if (s + 1 < Bc) {  // push on the chunk-local stack (scalars only: the vectors are the ring)
+                __syncwarp();
+                if (lane == 0) {
+                  double* ls = lstk + 5 * lvl;
+                  ls[0] = cur.w.m;
+                  ls[1] = cur.a.m;
+                  ls[2] = cur.pE;
+                  ls[3] = cur.plogp;
+                  lstk_i[3 * lvl] = cur.w.e;
+                  lstk_i[3 * lvl + 1] = cur.a.e;
+                  lstk_i[3 * lvl + 2] = pidx;
+                }
+                __syncwarp();
+              }
+            }
+            if (fail) break;
+            // ---- 5. the chunk is a subtree of level bc: merge it with the stack levels >= bc (generic path) -------------------
+            if (n_chunks > 1) {
+              double2 var[NP], cur_lp[NP], cur_ps[NP];
+#pragma unroll
+              for (int k = 0; k < NP; ++k) {
+                var[k] = s_var[k * 32];
+                cur_lp[k] = ring_p[k * 32];   // left edge = first leaf of the chunk
+                cur_ps[k] = psbuf[k * 32];    // p_sum of the whole chunk (Bc >= 2 here)
+              }
+              int lvl = bc;
+              for (unsigned cb = c; cb & 1u; cb >>= 1, ++lvl) {
+                __builtin_assume(lvl >= 1);
+                if (merge_level<G, NP>(sc, grp, ss, lvl, var, p, cur_lp, cur_ps, cur, free_slots, next_uniform())) {
+                  fail = 2;
+                  break;
+                }
+              }
+              if (fail) break;
+              if (c + 1 < n_chunks) {
+                __builtin_assume(lvl >= 1);
+                if (cur.pslot == kLeafProp) {  // the proposal leaves the position ring before the next chunk overwrites it
+                  cur.pslot = __ffs(free_slots) - 1;
+                  free_slots &= ~(1u << cur.pslot);
+#pragma unroll
+                  for (int k = 0; k < NP; ++k)
+                    sc.vec(vid_prop(cur.pslot))[k * G] = ring_q[(size_t)(pidx * NP + k) * 32];
+                }
+#pragma unroll
+                for (int k = 0; k < NP; ++k) {
+                  sc.vec(vid_stack(lvl, 0))[k * G] = cur_lp[k];
+                  sc.vec(vid_stack(lvl, 1))[k * G] = p[k];
+                  sc.vec(vid_stack(lvl, 2))[k * G] = cur_ps[k];
+                }
+                __syncwarp();
+                if (lane == 0) {
+                  ss->wm[lvl] = cur.w.m;
+                  ss->we[lvl] = cur.w.e;
+                  ss->am[lvl] = cur.a.m;
+                  ss->ae[lvl] = cur.a.e;
+                  ss->pE[lvl] = cur.pE;
+                  ss->plogp[lvl] = cur.plogp;
+                  ss->pslot[lvl] = cur.pslot;
+                }
+                __syncwarp();
+              } else {
+                // last chunk: its merged result is the doubling's subtree; keep its vectors for extend_top
+#pragma unroll
+                for (int k = 0; k < NP; ++k) {
+                  psbuf[k * 32] = cur_ps[k];
+                  ring_p[k * 32] = cur_lp[k];
+                }
+              }
+            }
+          }
+          ++tr.depth;            // nuts.py:315
+          tr.n_prop += n_leaves;  // :316
+          if (fail) {            // :318-319 -> :216-217
+            diverging = (fail == 1);
+            break;
+          }
+          // ---- top of _Tree.extend (nuts.py:321-340): T.left.p = ring_p[0] (or p), T.p_sum = psbuf[0] (or p) ------------------
+          {
+            double2 var[NP], cur_lp[NP], cur_ps[NP], qprop[NP];
+            const bool single = n_leaf_total == 1u;
+#pragma unroll
+            for (int k = 0; k < NP; ++k) {
+              var[k] = s_var[k * 32];
+              cur_lp[k] = single ? p[k] : ring_p[k * 32];
+              cur_ps[k] = single ? p[k] : psbuf[k * 32];
+              qprop[k] = q[k];
+            }
+            if (cur.pslot == kLeafProp) {
+#pragma unroll
+              for (int k = 0; k < NP; ++k) qprop[k] = ring_q[(size_t)(pidx * NP + k) * 32];
+            }
+            if (extend_top<G, NP>(sc, grp, tail, dir, var, qprop, p, cur_lp, cur_ps, cur, tr, next_uniform())) break;  // :340
+          }
+          if (d + 1 < max_depth) {
+            const int eb = (dir > 0 ? T_RQ : T_LQ);
+#pragma unroll
+            for (int k = 0; k < NP; ++k) {
+              sc.vec(tvid(tail, eb + 0))[k * G] = q[k];
+              sc.vec(tvid(tail, eb + 1))[k * G] = p[k];
+              sc.vec(tvid(tail, eb + 2))[k * G] = g[k];
+            }
+            reg_edge = dir;
+          } else {
+            reached_max = true;
+          }
+        }
+        const double accept_stat = mean_tree_accept(tr);
+#pragma unroll
+        for (int k = 0; k < NP; ++k) q[k] = sc.vec(tvid(tail, T_PROPQ))[k * G];  // hmc_step.end.q
+
+        double* const ad = a.adapt + (size_t)chain * LMC_ADAPT_STRIDE;
+        DualAvg da{__ldcg(ad + LMC_ADAPT_LOG_STEP), __ldcg(ad + LMC_ADAPT_LOG_BAR), __ldcg(ad + LMC_ADAPT_HBAR),
+                   __ldcg(ad + LMC_ADAPT_COUNT), __ldcg(ad + LMC_ADAPT_MU)};
+        WelfordScalars wel{__ldcg(ad + LMC_ADAPT_W_FG), __ldcg(ad + LMC_ADAPT_W_BG),
+                           (long long)__ldcg(ad + LMC_ADAPT_NSAMPLES), (long long)__ldcg(ad + LMC_ADAPT_WINDOW)};
+        if (adapt_step) dual_average_update(da, accept_stat, a.target_accept, a.gamma, a.k, a.t0);
+        if (tune && a.adapt_mass) {
+          const size_t off = (size_t)chain * a.ld;
+          double2 var[NP];
+#pragma unroll
+          for (int k = 0; k < NP; ++k) var[k] = s_var[k * 32];
+          welford_update<G, NP>(lane, D, ldh, a.mean_fg + off, a.rawvar_fg + off, a.mean_bg + off, a.rawvar_bg + off, q,
+                                var, wel, a.window_multiplier);
+          store_row<G, NP>(a.var + off, lane, ldh, var);
+        }
+        double* const trow = trace_row();
+        double* const srow = stats_row();
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+          const int j = lane + k * G;
+          if (2 * j < D) __stcs(trow + 2 * j, q[k].x);
+          if (2 * j + 1 < D) __stcs(trow + 2 * j + 1, q[k].y);
+        }
+        if (lane == 0) {
+          srow[LMC_STAT_DEPTH] = (double)tr.depth;
+          srow[LMC_STAT_TREE_SIZE] = (double)tr.n_prop;
+          srow[LMC_STAT_ACCEPT] = accept_stat;
+          srow[LMC_STAT_ENERGY] = tr.prop_E;
+          srow[LMC_STAT_ENERGY_ERROR] = tr.prop_E - E0;
+          srow[LMC_STAT_MAX_ENERGY_ERROR] = tr.max_dE;
+          srow[LMC_STAT_MODEL_LOGP] = tr.prop_logp;
+          srow[LMC_STAT_DIVERGING] = diverging ? 1.0 : 0.0;
+          srow[LMC_STAT_TUNE] = tune ? 1.0 : 0.0;
+          srow[LMC_STAT_STEP_SIZE] = exp_cold(da.log_step);
+          srow[LMC_STAT_STEP_SIZE_BAR] = exp_cold(da.log_bar);
+          srow[LMC_STAT_N_UNIFORMS] = (double)uc;
+          srow[LMC_STAT_REACHED_MAX_TREEDEPTH] = reached_max ? 1.0 : 0.0;
+        }
+        store_row<G, NP>(a.q + (size_t)chain * a.ld, lane, ldh, q);
+        __syncwarp();  // every lane has read the adaptation scalars before lane 0 overwrites them
+        if (lane == 0) {
+          ad[LMC_ADAPT_LOG_STEP] = da.log_step;
+          ad[LMC_ADAPT_LOG_BAR] = da.log_bar;
+          ad[LMC_ADAPT_HBAR] = da.hbar;
+          ad[LMC_ADAPT_COUNT] = da.count;
+          ad[LMC_ADAPT_W_FG] = wel.w_fg;
+          ad[LMC_ADAPT_W_BG] = wel.w_bg;
+          ad[LMC_ADAPT_NSAMPLES] = (double)wel.n_samples;
+          ad[LMC_ADAPT_WINDOW] = (double)wel.window;
+        }
+      }
+      if (lane == 0 && status) atomicOr(a.status + chain, status);
+    }
+    if (dead) {
+      const double nan = CUDART_NAN;
+      double* const trow = trace_row();
+      double* const srow = stats_row();
+      for (int e = lane; e < D; e += G) trow[e] = nan;
+      if (lane == 0)
+        for (int s = 0; s < LMC_NSTATS; ++s) srow[s] = nan;
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0 && t + 1 < a.n_trans) {
+      sv.prog[chain] = t + 1;
+      __threadfence();
+      const unsigned tk = atomicAdd(&sv.ctr[1], 1u);
+      *(volatile unsigned long long*)(sv.ring + (tk % (unsigned)a.n_chains)) =
+          ((unsigned long long)(tk + 1u) << 32) | (dead ? kDeadBit : 0u) | (unsigned)chain;
+    }
+  }
+}
+
+// vectors of global scratch per slot: tree stack + trajectory (as the other kernels) + the position ring of one chunk
+__host__ __device__ constexpr int ws_vecs_warp(int sdepth, int chunk) { return ws_vecs_nuts(sdepth) + chunk; }
+
+template <class Target, int NP, int B, int WPB, int MINB>
+int launch_warp(const lmc_sampler_args& a, const Target& tgt) {
+  using LY = WarpLayout<NP, B>;
+  constexpr int VS = LY::VS;
+  auto kern = sampler_warp_kernel<Target, NP, B, WPB, MINB>;
+  int dev = 0, n_sm = 0, smem_optin = 0;
+  LMC_CUDA(cudaGetDevice(&dev));
+  LMC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  LMC_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  const int sdepth = scratch_depth(a);
+  WarpCfg cfg;
+  cfg.ws_vecs = ws_vecs_warp(sdepth, B);
+  // tree-scratch vectors in shared memory: the three trajectory vectors every doubling touches (ids 0..2) when asked for
+  int n_smem = a.tune_smem_vecs >= 0 ? a.tune_smem_vecs : 0;
+  const int hot = vid_tail(sdepth);
+  if (n_smem > hot) n_smem = hot;
+  cfg.n_smem_vecs = n_smem;
+  cfg.slot_bytes = LY::kFixedBytes + n_smem * VS * 16;
+  const size_t smem = (size_t)WPB * cfg.slot_bytes;
+  if (smem > (size_t)smem_optin) return LMC_ERR_UNSUPPORTED;
+  LMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  LMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * WPB, smem));
+  if (occ < 1) return LMC_ERR_UNSUPPORTED;
+  long long blocks_needed = ((long long)a.n_chains + WPB - 1) / WPB;
+  long long grid = (long long)n_sm * occ;  // persistent: every CTA resident, a warp waiting on the ring never deadlocks
+  if (a.tune_max_slots > 0 && grid * WPB > a.tune_max_slots) grid = (a.tune_max_slots + WPB - 1) / WPB;
+  if (grid > blocks_needed) grid = blocks_needed;
+  if (grid < 1) grid = 1;
+  const long long need = (long long)sched_bytes(a.n_chains) + grid * WPB * (long long)cfg.ws_vecs * VS * 16;
+  if (need > a.workspace_bytes) return LMC_ERR_WORKSPACE;
+  if ((long long)a.n_chains * a.n_trans >= (1ll << 31)) return LMC_ERR_UNSUPPORTED;
+  sched_init_kernel<<<(a.n_chains + 255) / 256, 256, 0, (cudaStream_t)a.stream>>>(a.workspace, a.n_chains);
+  kern<<<(unsigned)grid, 32 * WPB, smem, (cudaStream_t)a.stream>>>(a, tgt, cfg);
+  LMC_CUDA(cudaGetLastError());
+  return LMC_OK;
+}
+
+}  // namespace lmc

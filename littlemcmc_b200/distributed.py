@@ -79,33 +79,27 @@ def gather_draw_chunks(local_trace, n_chains, draws_per_chunk, consume, group=No
 
 
 def _resolve_run(logp_dlogp_func, model_ndim, chains, random_seed, step, start, kwargs, group):
-    """Seeds, start and step method, identical on every rank: resolved on rank 0 and broadcast (the seed list depends
-    on the process-global NumPy stream when random_seed is None or an int: sampling.py:131-134)."""
+    """Seeds, start and step method, identical on every rank (sampling.py:131-134, 148-164)."""
     from . import sampling
     rank = dist.get_rank(group)
     # keywords of the drivers (sample / distributed.sample); everything else configures the step method (init_nuts)
     driver_keys = ("init", "cores", "progressbar", "chain_idx", "callback", "mp_ctx", "pickle_backend", "device",
                    "block", "return_device", "host_write", "stats_as", "_timing")
     nuts_kwargs = {k: kwargs.pop(k) for k in list(kwargs) if k not in driver_keys}
-    box = [None]
-    if rank == 0:
-        seeds = sampling._resolve_seeds(random_seed, chains)
-        start0 = None
-        if start is None:
-            # the reference draws ONE jittered start for all chains after reseeding with the first GLOBAL seed
-            # (sampling.py:148-164, 574-584)
-            start0, _ = sampling.init_nuts(logp_dlogp_func, model_ndim, init=kwargs.get("init", "auto"),
-                                           random_seed=seeds, **nuts_kwargs)
-        box[0] = (seeds, start0)
+    # the seed list depends on the process-global NumPy stream when random_seed is None: resolve it once, broadcast
+    box = [sampling._resolve_seeds(random_seed, chains) if rank == 0 else None]
     if dist.get_world_size(group) > 1:
         src = dist.get_global_rank(group, 0) if group is not None else 0
         dist.broadcast_object_list(box, src=src, group=group)
-    seeds, start0 = box[0]
-    if step is None:
-        _, step = sampling.init_nuts(logp_dlogp_func, model_ndim, init=kwargs.get("init", "auto"), random_seed=None,
-                                     **nuts_kwargs)
-    if start is None:
-        start = start0
+    seeds = box[0]
+    if step is None or start is None:
+        # the reference draws ONE jittered start for all chains after reseeding with the first GLOBAL seed, and seeds
+        # the potential's running mean with it (sampling.py:148-164, 574-587): a pure function of the seed list, so every
+        # rank computes the same start and the same step method whatever the number of ranks
+        start_, step_ = sampling.init_nuts(logp_dlogp_func, model_ndim, init=kwargs.get("init", "auto"),
+                                           random_seed=seeds, **nuts_kwargs)
+        step = step_ if step is None else step
+        start = start_ if start is None else start
     return seeds, np.asarray(start, dtype="d"), step
 
 

@@ -153,6 +153,7 @@ def _fill_base(a, kind, chains, *, n_trans, iter0, n_tune, params, seeds, tapes,
     a.tune_group = int(knobs.get("group", 0))
     a.tune_smem_vecs = int(knobs.get("smem_vecs", -1))
     a.tune_max_slots = int(knobs.get("max_slots", 0))
+    a.tune_chunk = int(knobs.get("chunk", 0))
     a.stream = (stream or torch.cuda.current_stream(dev)).cuda_stream
     return keep
 

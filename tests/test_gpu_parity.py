@@ -145,3 +145,28 @@ def test_lean_kernel_equals_default_kernel_on_chained_runs(name):
     for k in a.gpu_stats:
         assert np.array_equal(a.gpu_stats[k], b.gpu_stats[k], equal_nan=True), k
     assert np.array_equal(a.gpu_var, b.gpu_var) and np.array_equal(a.gpu_adapt, b.gpu_adapt)
+
+
+WARP_CASES = ["nuts_b1_d10", "nuts_diag_d37", "nuts_static_d100", "nuts_funnel_d10", "nuts_deep_d100",
+              "nuts_deep_funnel_d50", "nuts_deep_funnel_d10", "nuts_early_gt_max_d20"]
+
+
+@pytest.mark.parametrize("chunk", [4, 8, 16])
+@pytest.mark.parametrize("name", WARP_CASES)
+def test_warp_kernel_parity(name, chunk):
+    """The chunked warp-per-chain NUTS kernel (lmc_sampler_warp.cuh; the default up to 256 dimensions, forced here with
+    group=1) for every chunk length, with the trajectory vectors in the global workspace and in shared memory."""
+    for smem in (0, 3):
+        res = pu.run_case_on_gpu_and_oracle(name, knobs=dict(group=1, chunk=chunk, smem_vecs=smem))
+        pu.assert_parity(res, rtol=RTOL)
+
+
+@pytest.mark.parametrize("name", ["nuts_diag_d37", "nuts_funnel_d10"])
+def test_warp_kernel_agrees_with_the_one_warp_register_kernel(name):
+    """Chained adaptive runs of the chunked kernel and of the round-1 one-warp kernel (group=32): same decisions, floats
+    to rounding (the two sum their dot products in different orders), for as long as the chaotic feedback allows."""
+    a = pu.run_case_on_gpu_and_oracle(name, n_trans=12, chained=True, knobs=dict(group=1))
+    b = pu.run_case_on_gpu_and_oracle(name, n_trans=12, chained=True, knobs=dict(group=32))
+    for k in ("depth", "tree_size", "diverging"):
+        assert np.array_equal(a.gpu_stats[k], b.gpu_stats[k]), k
+    np.testing.assert_allclose(a.gpu_trace, b.gpu_trace, rtol=1e-8, atol=1e-11)
