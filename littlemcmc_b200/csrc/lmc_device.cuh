@@ -148,6 +148,8 @@ __device__ __forceinline__ double philox_uniform(uint64_t seed, int64_t it, uint
 #else
 #define LMC_COLD static __device__ __noinline__
 #endif
+// one Philox block of the uniform stream, out of line (the chunked kernel refills 32 uniforms at a time)
+LMC_COLD double philox_uniform_cold(uint64_t seed, int64_t it, uint32_t k) { return philox_uniform(seed, it, k); }
 // IEEE 1/sqrt(x) and a/b (two correctly rounded operations each, as NumPy computes them): ~45 instructions apiece
 LMC_COLD double inv_sqrt_cold(double x) { return 1.0 / sqrt(x); }
 LMC_COLD double div_cold(double a, double b) { return a / b; }

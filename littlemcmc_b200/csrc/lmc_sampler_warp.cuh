@@ -44,7 +44,8 @@ struct WarpLayout {
   static constexpr int oPs = oRingP + B * VS * 16;
   static constexpr int oVar = oPs + (B / 2) * VS * 16;
   static constexpr int oPart = oVar + VS * 16;
-  static constexpr int oVal = oPart + kRows * 32 * 8;
+  static constexpr int kRowLd = 34;                  // doubles per table row (32 + 2: conflict-free 128-bit row reads)
+  static constexpr int oVal = oPart + kRows * kRowLd * 8;
   // val: E[B], logp[B], dE[B], wm[B], pre[2B], dot[4B-6 (+pad)], local stack (kLog + 1) x 5 doubles, we[B] ints, lpidx ints
   static constexpr int nValD = 6 * B + (4 * B - 6 + 2) + 5 * (kLog + 1);
   static constexpr int oInts = oVal + nValD * 8;
@@ -53,7 +54,7 @@ struct WarpLayout {
   static constexpr int kFixedBytes = ((oSS + (int)sizeof(StackScalars)) + 15) & ~15;  // scratch vectors follow
 };
 
-template <class Target, int NP, int B, int WPB, int MINB>
+template <class Target, int NP, int B, int WPB, int MINB, bool TAPE>
 __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_sampler_args a, const Target tgt,
                                                                       const WarpCfg cfg) {
   using LY = WarpLayout<NP, B>;
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
   double2* const ring_p = reinterpret_cast<double2*>(base + LY::oRingP) + lane;  // [B][NP][32]
   double2* const psbuf = reinterpret_cast<double2*>(base + LY::oPs) + lane;     // [B/2][NP][32]
   double2* const s_var = reinterpret_cast<double2*>(base + LY::oVar) + lane;    // [NP][32]
-  double* const part = reinterpret_cast<double*>(base + LY::oPart);             // [kRows][32], column skewed by row
+  double* const part = reinterpret_cast<double*>(base + LY::oPart);             // [kRows][34]: row = value, column = lane
   double* const vE = reinterpret_cast<double*>(base + LY::oVal);
   double* const vLogp = vE + B;
   double* const vdE = vLogp + B;
@@ -96,40 +97,56 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
   // position ring of the current chunk: B vectors after the tree scratch of this slot (global, written once per leaf,
   // read back only for the one position per chunk that survives as a proposal)
   double2* const ring_q = sc.ws + (size_t)ws_vecs_nuts(sdepth) * VS + lane;
-  auto skew = [&](int row) -> double* { return part + row * 32 + ((lane + row) & 31); };
-  // sum of table row `row` over the 32 lanes' partials (fixed order: physical columns row, row+1, ..)
+  auto skew = [&](int row) -> double* { return part + row * LY::kRowLd + lane; };
+  // sum of table row `row` over the 32 lanes' partials (fixed order; four interleaved accumulators)
   auto row_sum = [&](int row) -> double {
-    const double* r = part + row * 32;
+    const double2* r = reinterpret_cast<const double2*>(part + row * LY::kRowLd);
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
-    for (int k = 0; k < 32; k += 4) {
-      s0 += r[(k + 0 + row) & 31];
-      s1 += r[(k + 1 + row) & 31];
-      s2 += r[(k + 2 + row) & 31];
-      s3 += r[(k + 3 + row) & 31];
+    for (int k = 0; k < 16; k += 2) {
+      const double2 x = r[k], y = r[k + 1];
+      s0 += x.x;
+      s1 += x.y;
+      s2 += y.x;
+      s3 += y.y;
     }
     return (s0 + s1) + (s2 + s3);
   };
 
+  // "sticky" launches: when every chain has its own resident warp there is nothing to schedule -- warp `slot` runs all
+  // the transitions of chain `slot` back to back, position and mass matrix stay on chip, and the FIFO's atomics, fences
+  // and state reloads (3 dependent L2 round trips + 2 membars per transition) disappear.  Same results either way.
+  const bool sticky = (unsigned)a.n_chains <= gridDim.x * (unsigned)WPB;
+  int t_next = 0;
+  bool sticky_dead = false;
+  double2 q[NP];
+
   for (;;) {
-    // ---- pop the next (chain, transition) unit (lmc_sampler.cuh: scheduler) ---------------------------------------------
+    // ---- the next (chain, transition) unit: own chain (sticky) or popped from the FIFO (lmc_sampler.cuh: scheduler) ----
     int chain = -1, t = 0;
-    if (lane == 0) {
-      const unsigned h = atomicAdd(&sv.ctr[0], 1u);
-      if (h < total_units) {
-        volatile unsigned long long* e = sv.ring + (h % (unsigned)a.n_chains);
-        unsigned long long v = *e;
-        while ((unsigned)(v >> 32) != h + 1u) {
-          __nanosleep(200);
-          v = *e;
-        }
-        __threadfence();
-        chain = (int)(unsigned)v;
-        t = *(volatile int*)(sv.prog + (chain & 0x7fffffff));
+    if (sticky) {
+      if (slot < a.n_chains && t_next < a.n_trans) {
+        chain = slot | (sticky_dead ? (int)kDeadBit : 0);
+        t = t_next++;
       }
+    } else {
+      if (lane == 0) {
+        const unsigned h = atomicAdd(&sv.ctr[0], 1u);
+        if (h < total_units) {
+          volatile unsigned long long* e = sv.ring + (h % (unsigned)a.n_chains);
+          unsigned long long v = *e;
+          while ((unsigned)(v >> 32) != h + 1u) {
+            __nanosleep(200);
+            v = *e;
+          }
+          __threadfence();
+          chain = (int)(unsigned)v;
+          t = *(volatile int*)(sv.prog + (chain & 0x7fffffff));
+        }
+      }
+      chain = __shfl_sync(FULL, chain, 0);
+      t = __shfl_sync(FULL, t, 0);
     }
-    chain = __shfl_sync(FULL, chain, 0);
-    t = __shfl_sync(FULL, t, 0);
     if (chain == -1) break;
     bool dead = ((unsigned)chain & kDeadBit) != 0u;
     chain &= 0x7fffffff;
@@ -141,17 +158,17 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
     int status = 0;
 
     if (!dead) {
-      double2 q[NP], p[NP], g[NP];
-      load_row_cg<G, NP>(a.q + (size_t)chain * a.ld, lane, ldh, q);
-      mask_tail<G, NP>(lane, D, q);
-      {
+      double2 p[NP], g[NP];
+      if (!sticky || t == 0) {
+        load_row_cg<G, NP>(a.q + (size_t)chain * a.ld, lane, ldh, q);
+        mask_tail<G, NP>(lane, D, q);
         double2 var[NP];
         load_row_cg<G, NP>(a.var + (size_t)chain * a.ld, lane, ldh, var);
         mask_tail<G, NP>(lane, D, var);
 #pragma unroll
         for (int k = 0; k < NP; ++k) s_var[k * 32] = var[k];
       }
-      const uint64_t seed = (a.rng.mode == LMC_RNG_PHILOX) ? a.rng.seeds[chain] : 0ull;
+      const uint64_t seed = TAPE ? 0ull : a.rng.seeds[chain];
       const long long it = a.iter0 + t;
       const bool tune = it < a.n_tune;
       const bool adapt_step = tune && a.adapt_step_size;
@@ -159,7 +176,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
       double u_lane = 0.0;
       auto next_uniform = [&]() -> double {
         double u;
-        if (a.rng.mode == LMC_RNG_TAPE) {
+        if constexpr (TAPE) {
           if ((long long)uc < a.rng.u_stride) {
             u = a.rng.uniforms[row * a.rng.u_stride + uc];
           } else {
@@ -167,7 +184,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
             status |= LMC_STATUS_TAPE_EXHAUSTED;
           }
         } else {
-          if ((uc & 31u) == 0u) u_lane = philox_uniform(seed, it, uc + (unsigned)lane);
+          if ((uc & 31u) == 0u) u_lane = philox_uniform_cold(seed, it, uc + (unsigned)lane);
           u = __shfl_sync(FULL, u_lane, (int)(uc & 31u));
         }
         ++uc;
@@ -176,7 +193,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
 
       // ---- p0 = potential.random()  (quadpotential.py:221-224 / 374-376) ------------------------------------------
       {
-        const double* normals_row = a.rng.mode == LMC_RNG_TAPE ? a.rng.normals + row * D : nullptr;
+        const double* normals_row = TAPE ? a.rng.normals + row * D : nullptr;
 #pragma unroll
         for (int k = 0; k < NP; ++k) {
           const int j = lane + k * G;
@@ -537,6 +554,8 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
           welford_update<G, NP>(lane, D, ldh, a.mean_fg + off, a.rawvar_fg + off, a.mean_bg + off, a.rawvar_bg + off, q,
                                 var, wel, a.window_multiplier);
           store_row<G, NP>(a.var + off, lane, ldh, var);
+#pragma unroll
+          for (int k = 0; k < NP; ++k) s_var[k * 32] = var[k];  // sticky launches keep the mass matrix on chip
         }
         double* const trow = trace_row();
         double* const srow = stats_row();
@@ -584,14 +603,19 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
       if (lane == 0)
         for (int s = 0; s < LMC_NSTATS; ++s) srow[s] = nan;
     }
-    __threadfence();
-    __syncwarp();
-    if (lane == 0 && t + 1 < a.n_trans) {
-      sv.prog[chain] = t + 1;
+    if (sticky) {
+      sticky_dead = dead;
+      __syncwarp();
+    } else {
       __threadfence();
-      const unsigned tk = atomicAdd(&sv.ctr[1], 1u);
-      *(volatile unsigned long long*)(sv.ring + (tk % (unsigned)a.n_chains)) =
-          ((unsigned long long)(tk + 1u) << 32) | (dead ? kDeadBit : 0u) | (unsigned)chain;
+      __syncwarp();
+      if (lane == 0 && t + 1 < a.n_trans) {
+        sv.prog[chain] = t + 1;
+        __threadfence();
+        const unsigned tk = atomicAdd(&sv.ctr[1], 1u);
+        *(volatile unsigned long long*)(sv.ring + (tk % (unsigned)a.n_chains)) =
+            ((unsigned long long)(tk + 1u) << 32) | (dead ? kDeadBit : 0u) | (unsigned)chain;
+      }
     }
   }
 }
@@ -599,11 +623,11 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
 // vectors of global scratch per slot: tree stack + trajectory (as the other kernels) + the position ring of one chunk
 __host__ __device__ constexpr int ws_vecs_warp(int sdepth, int chunk) { return ws_vecs_nuts(sdepth) + chunk; }
 
-template <class Target, int NP, int B, int WPB, int MINB>
-int launch_warp(const lmc_sampler_args& a, const Target& tgt) {
+template <class Target, int NP, int B, int WPB, int MINB, bool TAPE>
+int launch_warp_mode(const lmc_sampler_args& a, const Target& tgt) {
   using LY = WarpLayout<NP, B>;
   constexpr int VS = LY::VS;
-  auto kern = sampler_warp_kernel<Target, NP, B, WPB, MINB>;
+  auto kern = sampler_warp_kernel<Target, NP, B, WPB, MINB, TAPE>;
   int dev = 0, n_sm = 0, smem_optin = 0;
   LMC_CUDA(cudaGetDevice(&dev));
   LMC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
@@ -612,7 +636,7 @@ int launch_warp(const lmc_sampler_args& a, const Target& tgt) {
   WarpCfg cfg;
   cfg.ws_vecs = ws_vecs_warp(sdepth, B);
   // tree-scratch vectors in shared memory: the three trajectory vectors every doubling touches (ids 0..2) when asked for
-  int n_smem = a.tune_smem_vecs >= 0 ? a.tune_smem_vecs : 0;
+  int n_smem = a.tune_smem_vecs >= 0 ? a.tune_smem_vecs : 3;
   const int hot = vid_tail(sdepth);
   if (n_smem > hot) n_smem = hot;
   cfg.n_smem_vecs = n_smem;
@@ -635,6 +659,12 @@ int launch_warp(const lmc_sampler_args& a, const Target& tgt) {
   kern<<<(unsigned)grid, 32 * WPB, smem, (cudaStream_t)a.stream>>>(a, tgt, cfg);
   LMC_CUDA(cudaGetLastError());
   return LMC_OK;
+}
+
+template <class Target, int NP, int B, int WPB, int MINB>
+int launch_warp(const lmc_sampler_args& a, const Target& tgt) {
+  return a.rng.mode == LMC_RNG_TAPE ? launch_warp_mode<Target, NP, B, WPB, MINB, true>(a, tgt)
+                                    : launch_warp_mode<Target, NP, B, WPB, MINB, false>(a, tgt);
 }
 
 }  // namespace lmc

@@ -159,6 +159,9 @@ def test_warp_kernel_parity(name, chunk):
     for smem in (0, 3):
         res = pu.run_case_on_gpu_and_oracle(name, knobs=dict(group=1, chunk=chunk, smem_vecs=smem))
         pu.assert_parity(res, rtol=RTOL)
+    # fewer resident warps than chains: the FIFO scheduler instead of the sticky chain -> warp assignment
+    res = pu.run_case_on_gpu_and_oracle(name, knobs=dict(group=1, chunk=chunk, max_slots=1))
+    pu.assert_parity(res, rtol=RTOL)
 
 
 @pytest.mark.parametrize("name", ["nuts_diag_d37", "nuts_funnel_d10"])

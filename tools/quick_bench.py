@@ -1,5 +1,6 @@
-"""Scratch throughput probe (not the contract bench): NUTS on a diagonal Gaussian with in-kernel Philox, sweeping
-launch knobs.  Usage: python tools/quick_bench.py [C] [D] [n_trans] [group,group,...] [smem,smem,...]"""
+"""Scratch throughput probe (not the contract bench): NUTS with in-kernel Philox, sweeping launch knobs.
+Usage: python tools/quick_bench.py C D n_trans [groups] [smems] [slots] [chunks] [target=gauss|funnel] [depth]
+(lists are comma separated; group 0 = library default, 1 = chunked warp kernel, >= 32 register kernel, < 0 lean)"""
 import sys
 
 import numpy as np
@@ -9,41 +10,55 @@ sys.path.insert(0, ".")
 from littlemcmc_b200 import _lib as L  # noqa: E402
 from littlemcmc_b200 import engine  # noqa: E402
 
-C = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-D = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
-T = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-groups = [int(x) for x in sys.argv[4].split(",")] if len(sys.argv) > 4 else [0]
-smems = [int(x) for x in sys.argv[5].split(",")] if len(sys.argv) > 5 else [-1]
-slots = [int(x) for x in sys.argv[6].split(",")] if len(sys.argv) > 6 else [0]
+arg = sys.argv[1:]
+C = int(arg[0]) if len(arg) > 0 else 1024
+D = int(arg[1]) if len(arg) > 1 else 1000
+T = int(arg[2]) if len(arg) > 2 else 40
+groups = [int(x) for x in arg[3].split(",")] if len(arg) > 3 else [0]
+smems = [int(x) for x in arg[4].split(",")] if len(arg) > 4 else [-1]
+slots = [int(x) for x in arg[5].split(",")] if len(arg) > 5 else [0]
+chunks = [int(x) for x in arg[6].split(",")] if len(arg) > 6 else [0]
+target = arg[7] if len(arg) > 7 else "gauss"
+depth = int(arg[8]) if len(arg) > 8 else 10
+warm = int(arg[9]) if len(arg) > 9 else 100
 
 dev = "cuda:0"
-sigma = 10 ** np.linspace(-0.5, 0.5, D)
-tgt = engine.FusedTarget(L.TARGET_DIAG_GAUSSIAN, D, tau=1 / sigma**2)
+if target == "funnel":
+    tgt = engine.FusedTarget(L.TARGET_FUNNEL, D, v_scale=3.0)
+else:
+    sigma = 10 ** np.linspace(-0.5, 0.5, D)
+    tgt = engine.FusedTarget(L.TARGET_DIAG_GAUSSIAN, D, tau=1 / sigma**2)
 params = dict(adapt_mass=1, adapt_step_size=1, target_accept=0.8, gamma=0.05, k=0.75, t0=10, Emax=1000.0,
-              max_treedepth=10, early_max_treedepth=8)
+              max_treedepth=depth, early_max_treedepth=8)
 seeds = engine.seeds_tensor(np.arange(C) + 12345, dev)
 for g in groups:
     for sm in smems:
         for sl in slots:
-            ch = engine.DeviceChains(C, D, dev)
-            ch.reset_potential(np.ones(D), np.zeros(D), 10.0, 101)
-            ch.reset_step_adapt(0.25 / D**0.25)
-            ch.set_position(np.zeros(D))
-            knobs = dict(group=g, smem_vecs=sm, max_slots=sl)
-            # warm-up: 100 tuning transitions so step size / mass matrix are roughly adapted
-            engine.run_transitions(L.KIND_NUTS, ch, tgt, n_trans=100, iter0=0, n_tune=10**9, params=params,
-                                   seeds=seeds, knobs=knobs)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            tr, st = engine.run_transitions(L.KIND_NUTS, ch, tgt, n_trans=T, iter0=100, n_tune=10**9, params=params,
-                                            seeds=seeds, knobs=knobs)
-            e1.record()
-            torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1)
-            steps = float(st[:, :, L.STAT_TREE_SIZE].sum())
-            depth = float(st[:, :, L.STAT_DEPTH].mean())
-            acc = float(st[:, :, L.STAT_ACCEPT].mean())
-            print("C=%d D=%d T=%d group=%d smem=%d slots=%d: %.2f ms  %.3e leapfrog/s  (mean depth %.2f, accept %.3f, "
-                  "alg %.1f GB/s)" % (C, D, T, g, sm, sl, ms, steps / ms * 1e3, depth, acc,
-                                     steps / ms * 1e3 * 48 * D / 1e9), flush=True)
+            for ck in chunks:
+                ch = engine.DeviceChains(C, D, dev)
+                ch.reset_potential(np.ones(D), np.zeros(D), 10.0, 101)
+                ch.reset_step_adapt(0.25 / D**0.25)
+                ch.set_position(np.zeros(D))
+                knobs = dict(group=g, smem_vecs=sm, max_slots=sl, chunk=ck)
+                try:
+                    # warm-up: tuning transitions so step size / mass matrix are roughly adapted
+                    engine.run_transitions(L.KIND_NUTS, ch, tgt, n_trans=warm, iter0=0, n_tune=10**9, params=params,
+                                           seeds=seeds, knobs=knobs)
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    tr, st = engine.run_transitions(L.KIND_NUTS, ch, tgt, n_trans=T, iter0=warm, n_tune=10**9,
+                                                    params=params, seeds=seeds, knobs=knobs)
+                    e1.record()
+                    torch.cuda.synchronize()
+                except Exception as e:  # unsupported shape
+                    print("C=%d D=%d group=%d smem=%d slots=%d chunk=%d: %s" % (C, D, g, sm, sl, ck, e), flush=True)
+                    continue
+                ms = e0.elapsed_time(e1)
+                steps = float(st[:, :, L.STAT_TREE_SIZE].sum())
+                print("C=%d D=%d T=%d %s group=%d smem=%d slots=%d chunk=%d: %.2f ms  %.3e leapfrog/s  (depth %.2f max %d, "
+                      "accept %.3f, div %d, alg %.1f GB/s = %.3f of 6457)"
+                      % (C, D, T, target, g, sm, sl, ck, ms, steps / ms * 1e3, float(st[:, :, L.STAT_DEPTH].mean()),
+                         int(st[:, :, L.STAT_DEPTH].max()), float(st[:, :, L.STAT_ACCEPT].mean()),
+                         int(st[:, :, L.STAT_DIVERGING].sum()), steps / ms * 1e3 * 48 * D / 1e9,
+                         steps / ms * 1e3 * 48 * D / 1e9 / 6457.4), flush=True)
