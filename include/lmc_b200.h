@@ -242,6 +242,27 @@ int lmc_callback_begin(int32_t kind, const lmc_callback_args* args);
 int lmc_callback_advance(int32_t kind, const lmc_callback_args* args);
 
 /*
+ * Device-driven callback loop.  The host loop above costs a launch group and, now and then, a host synchronisation per
+ * gradient evaluation; here the whole `while (*n_running > 0)` runs on the GPU as ONE graph launch: a CUDA-graph WHILE
+ * conditional node whose body is the caller's captured iteration(s) -- `body_graph`, a cudaGraph_t holding one or more
+ * repetitions of [the caller's logp/grad op on q_eval -> lmc_callback_advance], captured by the caller on its own stream
+ * (torch.cuda.graph) -- followed by a one-thread kernel that reads *n_running and sets the loop condition.  No host
+ * involvement between the first and the last gradient evaluation.
+ *   lmc_callback_begin(kind, &c);                                    // as above (outside the graph)
+ *   lmc_callback_loop_create(body_graph, c.n_running, iters, max_iters, &loop);
+ *   lmc_callback_loop_launch(loop, stream);                           // asynchronous; the run is over when it completes
+ *   lmc_callback_loop_destroy(loop);                                  // after the stream has drained
+ * `iters` (device int32, zeroed by create's caller) counts executed bodies; the loop also stops after `max_iters`
+ * bodies (a safety net: *n_running is then still > 0 and the caller reports it).  The body graph is cloned: the caller
+ * may destroy its own copy after create.
+ */
+typedef struct lmc_callback_loop lmc_callback_loop;
+int lmc_callback_loop_create(void* body_graph, const int32_t* n_running, int32_t* iters, int64_t max_iters,
+                             lmc_callback_loop** loop_out);
+int lmc_callback_loop_launch(lmc_callback_loop* loop, void* stream);
+int lmc_callback_loop_destroy(lmc_callback_loop* loop);
+
+/*
  * Dense-mass mode: transitions with a DENSE mass matrix -- QuadPotentialFull / QuadPotentialFullInv /
  * QuadPotentialFullAdapt (quadpotential.py:390-615).  With a dense matrix three things are batched operations over
  * chains that cannot live inside one chain's thread group: the gradient (as in callback mode), the velocity

@@ -76,6 +76,9 @@ SYMBOLS = {
     "lmc_callback_state_bytes": (_I64, [_I32, _I32, _I32, _I32]),
     "lmc_callback_begin": (C.c_int, [_I32, C.POINTER(CallbackArgs)]),
     "lmc_callback_advance": (C.c_int, [_I32, C.POINTER(CallbackArgs)]),
+    "lmc_callback_loop_create": (C.c_int, [_P, _P, _P, _I64, C.POINTER(_P)]),
+    "lmc_callback_loop_launch": (C.c_int, [_P, _P]),
+    "lmc_callback_loop_destroy": (C.c_int, [_P]),
     "lmc_dense_state_bytes": (_I64, [_I32, _I32, _I32, _I32]),
     "lmc_dense_begin": (C.c_int, [_I32, C.POINTER(DenseArgs)]),
     "lmc_dense_advance": (C.c_int, [_I32, C.POINTER(DenseArgs)]),

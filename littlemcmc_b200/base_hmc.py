@@ -120,7 +120,7 @@ class BaseHMC:
         elif fused is not None:
             tr, st = engine.run_transitions(self._kind, self._chains, fused, knobs=self._knobs, events=events, **common)
         else:
-            graph = bool(getattr(self._logp_dlogp_func, "cuda_graph", False))
+            graph = getattr(self._logp_dlogp_func, "cuda_graph", False)
             if events is not None:
                 events[0].record()
             tr, st = engine.run_transitions_callback(self._kind, self._chains, self._logp_dlogp_func, cuda_graph=graph,

@@ -435,3 +435,65 @@ extern "C" int lmc_callback_advance(int32_t kind, const lmc_callback_args* c) {
   return kind == lmc::KIND_NUTS ? lmc::cb_launch<lmc::KIND_NUTS>(*c, vec_off, n_vecs, G, NP)
                                 : lmc::cb_launch<lmc::KIND_HMC>(*c, vec_off, n_vecs, G, NP);
 }
+
+// ---- device-driven loop: WHILE conditional graph node around the caller's captured iteration(s) ---------------------------
+namespace lmc {
+__global__ void cb_loop_cond_kernel(cudaGraphConditionalHandle handle, const int32_t* n_running, int32_t* iters,
+                                    long long max_iters) {
+  const int it = ++(*iters);
+  cudaGraphSetConditional(handle, (*n_running > 0 && (long long)it < max_iters) ? 1u : 0u);
+}
+}  // namespace lmc
+
+struct lmc_callback_loop {
+  cudaGraph_t graph;
+  cudaGraphExec_t exec;
+};
+
+extern "C" int lmc_callback_loop_create(void* body_graph, const int32_t* n_running, int32_t* iters, int64_t max_iters,
+                                        lmc_callback_loop** loop_out) {
+  if (!body_graph || !n_running || !iters || !loop_out || max_iters < 1) return LMC_ERR_BADARG;
+  cudaGraph_t parent = nullptr;
+  LMC_CUDA(cudaGraphCreate(&parent, 0));
+  cudaGraphConditionalHandle handle;
+  // default value 1 at every launch: the body runs at least once (do-while on the chains still running)
+  LMC_CUDA(cudaGraphConditionalHandleCreate(&handle, parent, 1, cudaGraphCondAssignDefault));
+  cudaGraphNodeParams wp = {};
+  wp.type = cudaGraphNodeTypeConditional;
+  wp.conditional.handle = handle;
+  wp.conditional.type = cudaGraphCondTypeWhile;
+  wp.conditional.size = 1;
+  cudaGraphNode_t while_node;
+  LMC_CUDA(cudaGraphAddNode(&while_node, parent, nullptr, 0, &wp));
+  cudaGraph_t body = wp.conditional.phGraph_out[0];
+  cudaGraphNode_t child;
+  LMC_CUDA(cudaGraphAddChildGraphNode(&child, body, nullptr, 0, (cudaGraph_t)body_graph));  // clones body_graph
+  long long mi = (long long)max_iters;
+  void* kargs[] = {&handle, &n_running, &iters, &mi};
+  cudaKernelNodeParams kp = {};
+  kp.func = (void*)lmc::cb_loop_cond_kernel;
+  kp.gridDim = dim3(1);
+  kp.blockDim = dim3(1);
+  kp.kernelParams = kargs;
+  cudaGraphNode_t cond;
+  LMC_CUDA(cudaGraphAddKernelNode(&cond, body, &child, 1, &kp));
+  cudaGraphExec_t exec = nullptr;
+  LMC_CUDA(cudaGraphInstantiate(&exec, parent, 0));
+  lmc_callback_loop* loop = new lmc_callback_loop{parent, exec};
+  *loop_out = loop;
+  return LMC_OK;
+}
+
+extern "C" int lmc_callback_loop_launch(lmc_callback_loop* loop, void* stream) {
+  if (!loop) return LMC_ERR_BADARG;
+  LMC_CUDA(cudaGraphLaunch(loop->exec, (cudaStream_t)stream));
+  return LMC_OK;
+}
+
+extern "C" int lmc_callback_loop_destroy(lmc_callback_loop* loop) {
+  if (!loop) return LMC_OK;
+  cudaGraphExecDestroy(loop->exec);
+  cudaGraphDestroy(loop->graph);
+  delete loop;
+  return LMC_OK;
+}

@@ -13,6 +13,7 @@ from . import _lib as L
 
 
 _GRAPH_RES = {}   # device -> (side stream, CUDA-graph memory pool) of callback mode
+_GRAPH_KEEP = {}  # device -> most recent captured graph (keeps the shared pool in use)
 
 # launches of this library's kernels enqueued by this process (bench.py reports the count inside its timed region)
 LAUNCH_COUNT = {"kernels": 0}
@@ -293,13 +294,18 @@ class CallbackRun:
         LAUNCH_COUNT["kernels"] += 1
 
     def run(self, cuda_graph=False, iters_per_graph=None, poll=4):
+        """`cuda_graph`: False = eager host loop; True / "device" = ONE graph launch whose WHILE conditional node loops
+        on the device until every chain has finished (lmc_callback_loop_*); "replay" = graphs of `iters_per_graph`
+        iterations replayed from the host with one synchronisation per replay."""
         dev = self.chains.device
         with torch.cuda.device(dev):
             self.begin()
-            if iters_per_graph is None:
-                iters_per_graph = 8
-            if cuda_graph:
-                self._run_graphed(iters_per_graph)
+            if cuda_graph in (True, "device"):
+                self._run_device_loop(iters_per_graph or 2)
+            elif cuda_graph == "replay":
+                self._run_graphed(iters_per_graph or 8)
+            elif cuda_graph:
+                raise ValueError("cuda_graph must be False, True, 'device' or 'replay'")
             else:
                 ev, it = None, 0
                 while it < self.max_iters:
@@ -317,7 +323,8 @@ class CallbackRun:
                     raise L.LmcError("callback mode: chains still running after %d gradient evaluations" % it)
         return self.trace, self.stats
 
-    def _run_graphed(self, iters_per_graph):
+    def _capture_iterations(self, n_iters, keep_graph):
+        """Capture `n_iters` x (callback + advance) on torch's capture stream.  -> torch.cuda.CUDAGraph"""
         dev = self.chains.device
         # one side stream and ONE graph memory pool per device, shared by every capture of this process: a fresh
         # pool per graph means cudaMalloc at capture and a synchronising cudaFree when the graph dies, every call
@@ -329,12 +336,48 @@ class CallbackRun:
         with torch.cuda.stream(side):       # warm the callback up outside capture (lazy init, autotune, allocations)
             evaluate_callback(self.callback, self.q_eval[:, :self.chains.ndim])
         torch.cuda.current_stream(dev).wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
+        graph = torch.cuda.CUDAGraph(keep_graph=True) if keep_graph else torch.cuda.CUDAGraph()
         before = self.n_evals
-        with torch.cuda.graph(graph, pool=pool):
-            for _ in range(iters_per_graph):
-                self.iteration()
+        # capture_begin / capture_end directly: the torch.cuda.graph context manager also runs gc.collect(),
+        # empty_cache() and a device synchronisation on entry (tens of milliseconds per run, measured)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            graph.capture_begin(pool=pool)
+            try:
+                for _ in range(n_iters):
+                    self.iteration()
+            finally:
+                graph.capture_end()
+        torch.cuda.current_stream(dev).wait_stream(side)
         self.n_evals = before
+        # the shared pool must never lose its last user between two captures (the allocator retires a pool whose use
+        # count drops to zero and asserts if it is handed out again): keep the newest graph of this device alive
+        _GRAPH_KEEP[key] = graph
+        return graph
+
+    def _run_device_loop(self, iters_per_body):
+        """The whole run as one graph launch: WHILE(n_running > 0) { callback; advance; } on the device."""
+        dev = self.chains.device
+        graph = self._capture_iterations(iters_per_body, keep_graph=True)
+        iters = torch.zeros(1, dtype=torch.int32, device=dev)
+        loop = C.c_void_p()
+        max_bodies = (self.max_iters + iters_per_body - 1) // iters_per_body
+        L.check(self.lib.lmc_callback_loop_create(C.c_void_p(int(graph.raw_cuda_graph())), _ptr(self.n_running),
+                                                  _ptr(iters), max_bodies, C.byref(loop)), "lmc_callback_loop_create")
+        try:
+            stream = torch.cuda.current_stream(dev)
+            L.check(self.lib.lmc_callback_loop_launch(loop, C.c_void_p(stream.cuda_stream)), "lmc_callback_loop_launch")
+            left, done = int(self.n_running.item()), int(iters.item())       # the one synchronisation of the run
+        finally:
+            torch.cuda.synchronize(dev)
+            self.lib.lmc_callback_loop_destroy(loop)
+        self.n_evals += done * iters_per_body
+        LAUNCH_COUNT["kernels"] += done * (iters_per_body + 1)               # advance kernels + the loop-condition kernel
+        if left != 0:
+            raise L.LmcError("callback mode: chains still running after %d gradient evaluations" % (done * iters_per_body))
+
+    def _run_graphed(self, iters_per_graph):
+        graph = self._capture_iterations(iters_per_graph, keep_graph=False)
         it = 0
         while it < self.max_iters:
             graph.replay()

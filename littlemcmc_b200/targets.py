@@ -89,12 +89,17 @@ class TorchBatched:
 
     It is evaluated on the current CUDA stream between two launches of the sampler's state-machine kernel (callback
     mode, csrc/lmc_callback.cu): one call per leapfrog step for ALL chains, instead of the reference's one call per
-    leapfrog step per chain (integration.py:115).  ``cuda_graph=True`` captures (callback + kernel) x 8 in a CUDA graph
-    and replays it; the callback must then be capture-safe (no host syncs, no data-dependent shapes)."""
+    leapfrog step per chain (integration.py:115).  ``cuda_graph=True`` (= ``"device"``) captures (callback + kernel) in
+    a CUDA graph and runs it as the body of a WHILE conditional node: the whole run is ONE graph launch that loops on the
+    device until every chain has finished -- no host round trip per gradient.  ``cuda_graph="replay"``: graphs of 8
+    iterations replayed from the host.  Either way the callback must be capture-safe (no host syncs, no data-dependent
+    shapes)."""
 
     def __init__(self, fn, cuda_graph=False):
         self.fn = fn
-        self.cuda_graph = bool(cuda_graph)
+        if cuda_graph not in (False, True, "device", "replay"):
+            raise ValueError("cuda_graph must be False, True, 'device' or 'replay'")
+        self.cuda_graph = cuda_graph
 
     def __call__(self, q):
         return self.fn(q)

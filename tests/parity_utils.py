@@ -162,7 +162,8 @@ def _launch(case, ch, tgt, callback, **kw):
     if callback is None:
         return engine.run_transitions(_kind(case), ch, tgt, **kw)
     kw.pop("knobs", None)
-    return engine.run_transitions_callback(_kind(case), ch, callback, **kw)
+    return engine.run_transitions_callback(_kind(case), ch, callback, cuda_graph=getattr(callback, "cuda_graph", False),
+                                           **kw)
 
 
 def _kind(case):
@@ -237,8 +238,9 @@ def gpu_run_transitionwise(case, ora, knobs=None, device="cuda:0", callback=None
 
 def run_case_on_gpu_and_oracle(name, n_trans=None, knobs=None, device="cuda:0", chained=False,
                                chunks=1, callback=None, overrides=None) -> ParityResult:
-    """`callback`: None = fused kernels; "torch" / "torch-graph" = callback mode with the case's density as a batched
-    torch op (eager / CUDA graph); "numpy" = callback mode with the oracle's per-chain NumPy callable."""
+    """`callback`: None = fused kernels; "torch" / "torch-graph" / "torch-replay" = callback mode with the case's density
+    as a batched torch op (eager host loop / device-driven WHILE graph / replayed graphs); "numpy" = callback mode with
+    the oracle's per-chain NumPy callable."""
     from littlemcmc_b200 import _lib as L
     case, _ = gc.load(name)
     case = truncate_case(case, n_trans)
@@ -246,8 +248,9 @@ def run_case_on_gpu_and_oracle(name, n_trans=None, knobs=None, device="cuda:0", 
         case = dict(case, **overrides)
     ora = oracle_run(case)
     table = NUTS_STATS if str(case["kind"]) == "nuts" else HMC_STATS
-    if callback in ("torch", "torch-graph"):
-        callback = torch_callback(case, device, cuda_graph=(callback == "torch-graph"))
+    if callback in ("torch", "torch-graph", "torch-replay"):
+        callback = torch_callback(case, device, cuda_graph={"torch": False, "torch-graph": True,
+                                                            "torch-replay": "replay"}[callback])
     elif callback == "numpy":
         callback = gc.target_fn(case)()
     if chained:

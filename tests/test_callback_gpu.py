@@ -13,6 +13,12 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-9
 
 
+def test_device_loop_transition_level_parity_deep_trees():
+    """Depth-10 trees through the device-driven loop: ~1000 loop bodies per transition without the host."""
+    res = pu.run_case_on_gpu_and_oracle("nuts_deep_d100", callback="torch-graph")
+    pu.assert_parity(res, rtol=RTOL)
+
+
 @pytest.mark.parametrize("name", gc.CASE_NAMES)
 def test_callback_transition_level_parity(name):
     case, _ = gc.load(name)
@@ -43,11 +49,13 @@ def test_callback_hmc_config1_statistics():
     pu.assert_parity(res, rtol=1e-6, atol=1e-9)
 
 
+@pytest.mark.parametrize("mode", ["torch-graph", "torch-replay"])
 @pytest.mark.parametrize("name", ["nuts_diag_d37", "nuts_funnel_d10", "hmc_static_d50"])
-def test_cuda_graph_equals_eager(name):
-    """(callback + advance) x 8 captured in a CUDA graph and replayed == the eager loop, bit for bit."""
+def test_cuda_graph_equals_eager(name, mode):
+    """The device-driven loop (ONE graph launch: WHILE n_running > 0 { callback; advance } as a conditional node,
+    lmc_callback_loop_*) and the replayed graphs of 8 iterations == the eager host loop, bit for bit."""
     eager = pu.run_case_on_gpu_and_oracle(name, n_trans=40, chained=True, callback="torch")
-    graph = pu.run_case_on_gpu_and_oracle(name, n_trans=40, chained=True, callback="torch-graph")
+    graph = pu.run_case_on_gpu_and_oracle(name, n_trans=40, chained=True, callback=mode)
     assert np.array_equal(eager.gpu_trace, graph.gpu_trace)
     for k in eager.gpu_stats:
         assert np.array_equal(eager.gpu_stats[k], graph.gpu_stats[k], equal_nan=True), k
