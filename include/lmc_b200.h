@@ -19,7 +19,15 @@
 #ifndef LMC_B200_H
 #define LMC_B200_H
 
+#ifdef __CUDACC_RTC__ /* run-time compilation of a user target (lmc_user_kernel_build): no host headers */
+typedef signed int int32_t;
+typedef unsigned int uint32_t;
+typedef long int64_t;
+typedef unsigned long uint64_t;
+typedef unsigned long uintptr_t;
+#else
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -185,6 +193,28 @@ int lmc_nuts_sample(const lmc_sampler_args* args);
 
 /* Same for HamiltonianMC._astep -> _hamiltonian_step (hmc.py:140-182). */
 int lmc_hmc_sample(const lmc_sampler_args* args);
+
+/*
+ * User-written target densities inside the fused sampler kernels.  The reference calls an arbitrary Python
+ * `logp_dlogp_func` once per leapfrog (integration.py:62,115; base_hmc.py:34); here a density written as CUDA C++ -- a
+ * type with the `pre / grad / finish` protocol of the built-in targets (csrc/lmc_device.cuh, "built-in target
+ * densities") -- is compiled INTO the sampler kernel at run time (NVRTC, sm_100a) and runs at the speed of the built-in
+ * ones.  `source` defines `struct <type_name>`; the struct is passed to the kernel by value as `target_bytes`
+ * (conventionally its only member is `const double* params`, a device pointer to the density's parameters).
+ *   kind / ndim / chunk / tape: the launch the kernel is specialised for (KIND 0 = NUTS, 1 = HMC; chunk as
+ *   lmc_sampler_args.tune_chunk; tape != 0: randomness from tapes, else in-kernel Philox -- only the chunked kernel
+ *   (NUTS, ndim <= 256) is specialised on it);  include_dirs: where lmc_sampler*.cuh and lmc_b200.h live;
+ *   cache_path (nullable): the compiled cubin is stored there (+ ".name") and reused by later builds.
+ * lmc_user_kernel_log(): compiler output of this thread's last build.  lmc_user_sample == lmc_nuts_sample /
+ * lmc_hmc_sample with args->target ignored.
+ */
+typedef struct lmc_user_kernel lmc_user_kernel;
+int lmc_user_kernel_build(const char* source, const char* type_name, int32_t kind, int32_t ndim, int32_t chunk,
+                          int32_t tape, const char* const* include_dirs, int32_t n_include_dirs, const char* cache_path,
+                          lmc_user_kernel** out);
+const char* lmc_user_kernel_log(void);
+int lmc_user_sample(lmc_user_kernel* kernel, const lmc_sampler_args* args, const void* target_bytes);
+int lmc_user_kernel_destroy(lmc_user_kernel* kernel);
 
 /* CpuLeapfrogIntegrator.compute_state (integration.py:52-66) for all chains with a built-in target:
  * g = dlogp(q), v = var*p, energy = 0.5 p.v - logp.  var_stride = ld for per-chain var, 0 to broadcast one row. */

@@ -79,6 +79,11 @@ SYMBOLS = {
     "lmc_callback_loop_create": (C.c_int, [_P, _P, _P, _I64, C.POINTER(_P)]),
     "lmc_callback_loop_launch": (C.c_int, [_P, _P]),
     "lmc_callback_loop_destroy": (C.c_int, [_P]),
+    "lmc_user_kernel_build": (C.c_int, [C.c_char_p, C.c_char_p, _I32, _I32, _I32, _I32, C.POINTER(C.c_char_p), _I32,
+                                        C.c_char_p, C.POINTER(_P)]),
+    "lmc_user_kernel_log": (C.c_char_p, []),
+    "lmc_user_sample": (C.c_int, [_P, C.POINTER(SamplerArgs), _P]),
+    "lmc_user_kernel_destroy": (C.c_int, [_P]),
     "lmc_dense_state_bytes": (_I64, [_I32, _I32, _I32, _I32]),
     "lmc_dense_begin": (C.c_int, [_I32, C.POINTER(DenseArgs)]),
     "lmc_dense_advance": (C.c_int, [_I32, C.POINTER(DenseArgs)]),

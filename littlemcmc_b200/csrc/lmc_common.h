@@ -2,7 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
-#include "../../include/lmc_b200.h"
+#include "lmc_b200.h"
 
 namespace lmc {
 void set_last_error(const char* what, cudaError_t err);

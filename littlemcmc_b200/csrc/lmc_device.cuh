@@ -17,11 +17,16 @@
 // size.  Dot products use FMA accumulation + a butterfly; like BLAS ddot in the reference their summation
 // order is unspecified, which is where the (<= few ulp) differences come from.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
+#else  // NVRTC (user targets compiled at run time): built-in declarations only
+#define CUDART_INF __longlong_as_double(0x7ff0000000000000LL)
+#define CUDART_NAN __longlong_as_double(0xfff8000000000000LL)
+#endif
 
-#include "../../include/lmc_b200.h"
+#include "lmc_b200.h"
 
 namespace lmc {
 

@@ -4,7 +4,7 @@
 
 namespace lmc {
 
-static int check_args(const lmc_sampler_args* a, int kind) {
+int check_sampler_args(const lmc_sampler_args* a, int kind, bool check_target) {
   if (!a) return LMC_ERR_BADARG;
   if (a->abi_version != LMC_ABI_VERSION) return LMC_ERR_BADARG;
   if (a->n_chains < 0 || a->ndim < 1 || a->n_trans < 0) return LMC_ERR_BADARG;
@@ -31,6 +31,7 @@ static int check_args(const lmc_sampler_args* a, int kind) {
   } else {
     if (a->max_steps < 1) return LMC_ERR_BADARG;
   }
+  if (!check_target) return LMC_OK;  // a user target compiled at run time (lmc_user.cu): args.target is ignored
   if (a->target.kind == LMC_TARGET_DIAG_GAUSSIAN) {
     if (!a->target.tau || ((uintptr_t)a->target.tau & 15)) return LMC_ERR_BADARG;
   } else if (a->target.kind != LMC_TARGET_FUNNEL) {
@@ -65,7 +66,7 @@ static int lean_group(const lmc_sampler_args* a, int kind) {
 }
 
 static int sample_entry(const lmc_sampler_args* a, int kind) {
-  const int rc = check_args(a, kind);
+  const int rc = check_sampler_args(a, kind, true);
   if (rc != LMC_OK) return rc;
   if (a->n_chains == 0 || a->n_trans == 0) return LMC_OK;
   if (a->target.kind == LMC_TARGET_DIAG_GAUSSIAN) {

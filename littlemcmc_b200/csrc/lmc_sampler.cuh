@@ -16,10 +16,9 @@
 // a vector.  The hottest scratch vectors (level-0/1 entries and the first proposal slots) live in shared
 // memory, the rest in an L2-resident global workspace.
 #pragma once
-#include <cuda_runtime.h>
-#include <stdint.h>
-
+#ifndef __CUDACC_RTC__
 #include "lmc_common.h"
+#endif
 #include "lmc_device.cuh"
 #include "lmc_tree.cuh"
 
@@ -430,6 +429,7 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
   }
 }
 
+#ifndef __CUDACC_RTC__
 // ---- host side: pick (G, NP), shared-memory split and grid; launch ---------------------------------------------------
 struct Shape { int G, NP; };
 
@@ -452,12 +452,13 @@ inline bool pick_shape(int ndim, int force_group, Shape* out) {
   return false;
 }
 
-template <class Target, int G, int NP, int KIND>
-int launch(const lmc_sampler_args& a, const Target& tgt) {
+// `kern`: the kernel to launch -- a __global__ function of this library, or a cudaKernel_t of a module compiled at run
+// time for a user target (lmc_user.cu); `tgt`: host pointer to the kernel's by-value target argument.
+template <int G, int NP, int KIND>
+int launch_kernel(const void* kern, const lmc_sampler_args& a, const void* tgt) {
   constexpr int BLOCK = block_threads<G>();
   constexpr int CPB = BLOCK / G;
   constexpr int VS = G * NP;
-  auto kern = sampler_kernel<Target, G, NP, KIND>;
   int dev = 0, n_sm = 0, smem_optin = 0;
   LMC_CUDA(cudaGetDevice(&dev));
   LMC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
@@ -498,9 +499,15 @@ int launch(const lmc_sampler_args& a, const Target& tgt) {
   if (need > a.workspace_bytes) return LMC_ERR_WORKSPACE;
   if ((long long)a.n_chains * a.n_trans >= (1ll << 31)) return LMC_ERR_UNSUPPORTED;  // 32-bit scheduler tickets
   sched_init_kernel<<<(a.n_chains + 255) / 256, 256, 0, (cudaStream_t)a.stream>>>(a.workspace, a.n_chains);
-  kern<<<(unsigned)grid, BLOCK, smem, (cudaStream_t)a.stream>>>(a, tgt, cfg);
+  void* kargs[] = {const_cast<lmc_sampler_args*>(&a), const_cast<void*>(tgt), &cfg};
+  LMC_CUDA(cudaLaunchKernel(kern, dim3((unsigned)grid), dim3(BLOCK), kargs, smem, (cudaStream_t)a.stream));
   LMC_CUDA(cudaGetLastError());
   return LMC_OK;
+}
+
+template <class Target, int G, int NP, int KIND>
+int launch(const lmc_sampler_args& a, const Target& tgt) {
+  return launch_kernel<G, NP, KIND>(reinterpret_cast<const void*>(sampler_kernel<Target, G, NP, KIND>), a, &tgt);
 }
 
 template <class Target, int KIND>
@@ -513,6 +520,6 @@ int dispatch_shape(const lmc_sampler_args& a, const Target& tgt) {
 #undef LMC_X
   return LMC_ERR_UNSUPPORTED;
 }
-
+#endif  // !__CUDACC_RTC__
 
 }  // namespace lmc

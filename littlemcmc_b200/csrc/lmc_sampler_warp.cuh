@@ -33,6 +33,9 @@ struct WarpCfg {
   int n_smem_vecs; // tree-scratch vectors kept in shared memory (ids < n_smem_vecs)
 };
 
+// vectors of global scratch per slot: tree stack + trajectory (as the other kernels) + the position ring of one chunk
+__host__ __device__ constexpr int ws_vecs_warp(int sdepth, int chunk) { return ws_vecs_nuts(sdepth) + chunk; }
+
 template <int NP, int B>
 struct WarpLayout {
   static constexpr int VS = 32 * NP;                 // pairs per vector
@@ -620,14 +623,14 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
   }
 }
 
-// vectors of global scratch per slot: tree stack + trajectory (as the other kernels) + the position ring of one chunk
-__host__ __device__ constexpr int ws_vecs_warp(int sdepth, int chunk) { return ws_vecs_nuts(sdepth) + chunk; }
 
-template <class Target, int NP, int B, int WPB, int MINB, bool TAPE>
-int launch_warp_mode(const lmc_sampler_args& a, const Target& tgt) {
+#ifndef __CUDACC_RTC__
+// `kern`: a sampler_warp_kernel instantiation of this library or a cudaKernel_t compiled at run time for a user target
+// (lmc_user.cu); `tgt`: host pointer to the kernel's by-value target argument.
+template <int NP, int B, int WPB>
+int launch_warp_kernel(const void* kern, const lmc_sampler_args& a, const void* tgt) {
   using LY = WarpLayout<NP, B>;
   constexpr int VS = LY::VS;
-  auto kern = sampler_warp_kernel<Target, NP, B, WPB, MINB, TAPE>;
   int dev = 0, n_sm = 0, smem_optin = 0;
   LMC_CUDA(cudaGetDevice(&dev));
   LMC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
@@ -635,7 +638,7 @@ int launch_warp_mode(const lmc_sampler_args& a, const Target& tgt) {
   const int sdepth = scratch_depth(a);
   WarpCfg cfg;
   cfg.ws_vecs = ws_vecs_warp(sdepth, B);
-  // tree-scratch vectors in shared memory: the three trajectory vectors every doubling touches (ids 0..2) when asked for
+  // tree-scratch vectors in shared memory: the three trajectory vectors every doubling touches (ids 0..2) by default
   int n_smem = a.tune_smem_vecs >= 0 ? a.tune_smem_vecs : 3;
   const int hot = vid_tail(sdepth);
   if (n_smem > hot) n_smem = hot;
@@ -656,9 +659,16 @@ int launch_warp_mode(const lmc_sampler_args& a, const Target& tgt) {
   if (need > a.workspace_bytes) return LMC_ERR_WORKSPACE;
   if ((long long)a.n_chains * a.n_trans >= (1ll << 31)) return LMC_ERR_UNSUPPORTED;
   sched_init_kernel<<<(a.n_chains + 255) / 256, 256, 0, (cudaStream_t)a.stream>>>(a.workspace, a.n_chains);
-  kern<<<(unsigned)grid, 32 * WPB, smem, (cudaStream_t)a.stream>>>(a, tgt, cfg);
+  void* kargs[] = {const_cast<lmc_sampler_args*>(&a), const_cast<void*>(tgt), &cfg};
+  LMC_CUDA(cudaLaunchKernel(kern, dim3((unsigned)grid), dim3(32 * WPB), kargs, smem, (cudaStream_t)a.stream));
   LMC_CUDA(cudaGetLastError());
   return LMC_OK;
+}
+
+template <class Target, int NP, int B, int WPB, int MINB, bool TAPE>
+int launch_warp_mode(const lmc_sampler_args& a, const Target& tgt) {
+  return launch_warp_kernel<NP, B, WPB>(reinterpret_cast<const void*>(sampler_warp_kernel<Target, NP, B, WPB, MINB, TAPE>),
+                                        a, &tgt);
 }
 
 template <class Target, int NP, int B, int WPB, int MINB>
@@ -666,5 +676,6 @@ int launch_warp(const lmc_sampler_args& a, const Target& tgt) {
   return a.rng.mode == LMC_RNG_TAPE ? launch_warp_mode<Target, NP, B, WPB, MINB, true>(a, tgt)
                                     : launch_warp_mode<Target, NP, B, WPB, MINB, false>(a, tgt);
 }
+#endif  // !__CUDACC_RTC__
 
 }  // namespace lmc

@@ -7,9 +7,6 @@
 // (velocities are recomputed as var*p, bit-identical to the stored ones) and an index into a small pool of
 // proposal-position vectors, so choosing a proposal moves an index, never a vector.
 #pragma once
-#include <cuda_runtime.h>
-#include <stdint.h>
-
 #include "lmc_device.cuh"
 
 namespace lmc {

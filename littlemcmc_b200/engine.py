@@ -108,6 +108,63 @@ class FusedTarget:
         return t
 
 
+class UserFusedTarget:
+    """A target density written by the user as CUDA C++ (protocol: csrc/lmc_device.cuh, "built-in target densities"),
+    compiled into the fused sampler kernel at run time (include/lmc_b200.h: lmc_user_kernel_build, NVRTC for sm_100a).
+    `source` defines `struct <type_name>` whose only data member is `const double* params`; `params` (host array,
+    float64) is uploaded once per device and its address handed to the kernel."""
+
+    def __init__(self, source, type_name, ndim, params=None):
+        self.source, self.type_name, self.ndim = str(source), str(type_name), int(ndim)
+        self.params_host = np.zeros(2) if params is None else np.ascontiguousarray(params, dtype=np.float64).ravel()
+        self._params_dev, self._kernels = {}, {}
+
+    @staticmethod
+    def cache_dir():
+        import os
+        import tempfile
+        d = os.environ.get("LMC_USER_CACHE") or os.path.join(os.path.expanduser("~"), ".cache", "littlemcmc_b200")
+        try:
+            os.makedirs(d, exist_ok=True)
+            return d
+        except OSError:
+            return tempfile.mkdtemp(prefix="littlemcmc_b200_")
+
+    def kernel(self, kind, chunk, tape):
+        """Handle of the sampler kernel specialised for (this target, kind, chunk, RNG mode): compiled on first use,
+        the cubin cached on disk under a hash of the source, the specialisation and the library's kernel headers."""
+        import hashlib
+        import os
+        key = (int(kind), int(chunk), bool(tape))
+        if key in self._kernels:
+            return self._kernels[key]
+        lib = L.load()
+        pkg = os.path.dirname(os.path.abspath(__file__))
+        dirs = [os.path.join(pkg, "csrc"), os.path.join(os.path.dirname(pkg), "include")]
+        h = hashlib.sha256(repr((self.source, self.type_name, self.ndim, key, L.ABI_VERSION)).encode())
+        for d in dirs:
+            for f in sorted(os.listdir(d)):
+                if f.endswith((".cuh", ".h")):
+                    h.update(open(os.path.join(d, f), "rb").read())
+        cache = os.path.join(self.cache_dir(), h.hexdigest()[:32] + ".cubin")
+        arr = (C.c_char_p * len(dirs))(*[d.encode() for d in dirs])
+        handle = C.c_void_p()
+        rc = lib.lmc_user_kernel_build(self.source.encode(), self.type_name.encode(), int(kind), self.ndim, int(chunk),
+                                       int(bool(tape)), arr, len(dirs), cache.encode(), C.byref(handle))
+        if rc != L.OK:
+            log = lib.lmc_user_kernel_log().decode(errors="replace")
+            raise L.LmcError("compiling the user target %r failed (%s):\n%s"
+                             % (self.type_name, L._ERR_NAMES.get(rc, rc), log or lib.lmc_last_error().decode()))
+        self._kernels[key] = handle
+        return handle
+
+    def target_bytes(self, device):
+        key = str(device)
+        if key not in self._params_dev:
+            self._params_dev[key] = torch.as_tensor(self.params_host, dtype=torch.float64, device=device)
+        return C.c_void_p(self._params_dev[key].data_ptr())
+
+
 def _fill_base(a, kind, chains, *, n_trans, iter0, n_tune, params, seeds, tapes, trace, stats, knobs, stream,
                step_size_override=None):
     """Fill an lmc_sampler_args (everything but target / workspace).  Returns the tensors that must outlive the launch."""
@@ -185,7 +242,13 @@ def run_transitions(kind, chains, target, *, n_trans, iter0, n_tune, params, see
         keep = _fill_base(a, kind, chains, n_trans=n_trans, iter0=iter0, n_tune=n_tune, params=params, seeds=seeds,
                           tapes=tapes, trace=trace, stats=stats, knobs=knobs, stream=stream,
                           step_size_override=step_size_override)
-        a.target = target.c_struct(dev)
+        user = isinstance(target, UserFusedTarget)
+        if user:
+            a.tune_group = 0                  # the kernel a user target is compiled into is the library's default choice
+            handle = target.kernel(kind, a.tune_chunk, tapes is not None)
+            tptr = target.target_bytes(dev)   # struct { const double* params; } passed by value
+        else:
+            a.target = target.c_struct(dev)
         nbytes = lib.lmc_workspace_bytes(kind, Cn, D, max(a.max_treedepth, a.early_max_treedepth), a.tune_group)
         if nbytes < 0:
             L.check(int(nbytes), "lmc_workspace_bytes")
@@ -195,10 +258,10 @@ def run_transitions(kind, chains, target, *, n_trans, iter0, n_tune, params, see
         launch_stream = stream or torch.cuda.current_stream(dev)
         if events is not None:
             events[0].record(launch_stream)
-        rc = fn(C.byref(a))
+        rc = lib.lmc_user_sample(handle, C.byref(a), C.byref(tptr)) if user else fn(C.byref(a))
         if events is not None:
             events[1].record(launch_stream)
-        L.check(rc, "lmc_nuts_sample" if kind == L.KIND_NUTS else "lmc_hmc_sample")
+        L.check(rc, "lmc_user_sample" if user else ("lmc_nuts_sample" if kind == L.KIND_NUTS else "lmc_hmc_sample"))
         LAUNCH_COUNT["kernels"] += 2      # sched_init_kernel + sampler_kernel
     for t in keep:  # tensors referenced by the enqueued kernel must outlive it on this stream
         t.record_stream(torch.cuda.current_stream(dev)) if t.is_cuda else None

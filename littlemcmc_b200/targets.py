@@ -9,7 +9,7 @@ Arbitrary callables are supported through :class:`TorchBatched` / the NumPy adap
 import numpy as np
 
 from . import _lib as L
-from .engine import FusedTarget
+from .engine import FusedTarget, UserFusedTarget
 
 
 class DiagGaussian:
@@ -82,6 +82,96 @@ class NealFunnel:
             g[:, 0] = -(v * inv_s2) + hs - half_nm1
             return -(0.5 * v * v * inv_s2) - hs - half_nm1 * v, g
         return TorchBatched(fn, cuda_graph=cuda_graph)
+
+
+class CudaTarget:
+    """A user-written density evaluated INSIDE the fused sampler kernels (no callback, no launch per gradient).
+
+    ``source`` is CUDA C++ defining ``struct <type_name>`` with the protocol of the built-in targets
+    (csrc/lmc_device.cuh): ``static constexpr int kPre``; ``pre<G,NP>(lane, D, q, out)`` partial sums the gradient needs
+    (if any); ``grad<G,NP>(lane, D, ldh, q, g, pre)`` writes this thread's gradient pairs and returns its partial of the
+    log-density sum; ``finish(sum, pre)`` the log density.  Its only data member is ``const double* params``; ``params``
+    is uploaded once.  The sampler kernel is compiled for sm_100a at first use (NVRTC) and cached on disk.
+    ``numpy_fn`` (optional) is the same density as a reference-style callable ``q[D] -> (logp, dlogp[D])``
+    (base_hmc.py:34), so that the object also drives the reference / the per-step integrator API."""
+
+    def __init__(self, source, type_name, ndim, params=None, numpy_fn=None):
+        self.ndim = int(ndim)
+        self.fused = UserFusedTarget(source, type_name, ndim, params)
+        self._numpy_fn = numpy_fn
+
+    def __call__(self, q):
+        if self._numpy_fn is None:
+            raise NotImplementedError("this CudaTarget was built without a NumPy callable (numpy_fn=...)")
+        return self._numpy_fn(q)
+
+
+_ELEMENTWISE_TEMPLATE = """
+struct %(name)s {
+  static constexpr int kPre = 0;
+  const double* params;  // [n_params][ld] rows, ld = ndim rounded up to even, padding 0
+  template <int G, int NP>
+  __device__ __forceinline__ void pre(int, int, const double2 (&)[NP], double (&)[2]) const {}
+  template <int G, int NP>
+  __device__ __forceinline__ double grad(int lane, int D, int ldh, const double2 (&q_)[NP], double2 (&g_)[NP],
+                                         const double (&)[2]) const {
+    double part = 0.0;
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      const int j = lane + k * G;
+      double2 gk = make_double2(0.0, 0.0);
+      if (j < ldh) {
+%(loads)s
+        if (2 * j < D) {
+          const double q = q_[k].x;
+%(bind_x)s
+          gk.x = (%(grad)s);
+          part += (%(logp)s);
+        }
+        if (2 * j + 1 < D) {
+          const double q = q_[k].y;
+%(bind_y)s
+          gk.y = (%(grad)s);
+          part += (%(logp)s);
+        }
+      }
+      g_[k] = gk;
+    }
+    return part;
+  }
+  __device__ __forceinline__ double finish(double sum, const double (&)[2]) const { return sum; }
+};
+"""
+
+
+class ElementwiseTarget(CudaTarget):
+    """Separable density ``logp(q) = sum_i f(q_i; theta_i)`` from two C expressions: ``logp`` = f and ``grad`` = df/dq,
+    written in terms of ``q`` and the names of ``params`` (a dict name -> array[ndim] or scalar).  Example (the built-in
+    diagonal Gaussian): ``ElementwiseTarget(D, logp="0.5 * q * (-(tau * q))", grad="-(tau * q)", params={"tau": tau})``.
+    The same expressions are evaluated with NumPy for the reference-style callable (exp, log, sqrt, tanh ... map to
+    numpy's).  Multiply-adds are not contracted (-fmad=false), as in NumPy."""
+
+    def __init__(self, ndim, logp, grad, params=None):
+        import hashlib
+        params = {k: np.broadcast_to(np.asarray(v, dtype="d"), (int(ndim),)).copy() for k, v in (params or {}).items()}
+        names = sorted(params)
+        ld = int(ndim) + (int(ndim) & 1)
+        blob = np.zeros((max(1, len(names)), ld))
+        for i, n in enumerate(names):
+            blob[i, :ndim] = params[n]
+        name = "LmcElementwise_" + hashlib.sha256(repr((logp, grad, names)).encode()).hexdigest()[:12]
+        loads = "\n".join("        const double2 %s_2 = reinterpret_cast<const double2*>(params + %d * 2 * (size_t)ldh)[j];"
+                          % (n, i) for i, n in enumerate(names))
+        bind = lambda c: "\n".join("          const double %s = %s_2.%s;" % (n, n, c) for n in names)  # noqa: E731
+        src = _ELEMENTWISE_TEMPLATE % dict(name=name, loads=loads, bind_x=bind("x"), bind_y=bind("y"), grad=grad, logp=logp)
+        env = {k: getattr(np, k) for k in ("exp", "log", "sqrt", "tanh", "sin", "cos", "log1p", "expm1", "fabs")}
+
+        def numpy_fn(q):
+            scope = dict(env, q=np.asarray(q, dtype="d"), **params)
+            return float(np.sum(eval(logp, {"__builtins__": {}}, scope))), np.asarray(eval(grad, {"__builtins__": {}}, scope),
+                                                                                       dtype="d") * np.ones(int(ndim))
+        super().__init__(src, name, ndim, params=blob, numpy_fn=numpy_fn)
+        self.logp_expr, self.grad_expr, self.params = logp, grad, params
 
 
 class TorchBatched:

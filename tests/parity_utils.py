@@ -178,14 +178,14 @@ def _read_state(ch):
     return ch.q[:, :D].cpu().numpy(), ch.var[:, :D].cpu().numpy(), wel.cpu().numpy(), ch.adapt[:, :9].cpu().numpy()
 
 
-def gpu_run_chained(case, tapes, chunks=1, knobs=None, device="cuda:0", callback=None):
+def gpu_run_chained(case, tapes, chunks=1, knobs=None, device="cuda:0", callback=None, target=None):
     """The whole run on the GPU, state carried on the device between `chunks` launches (run-level)."""
     import torch
     from littlemcmc_b200 import engine
     normals, uniforms, _ = tapes
     Cn, T, D = normals.shape
     ch = gpu_chains(case, Cn, device)
-    tgt, params = gpu_target(case), gpu_params(case)
+    tgt, params = target or gpu_target(case), gpu_params(case)
     bounds = np.linspace(0, T, chunks + 1).astype(int)
     traces, stats = [], []
     for lo, hi in zip(bounds[:-1], bounds[1:]):
@@ -199,7 +199,7 @@ def gpu_run_chained(case, tapes, chunks=1, knobs=None, device="cuda:0", callback
     return torch.cat(traces, 1).cpu().numpy(), torch.cat(stats, 1).cpu().numpy(), ch
 
 
-def gpu_run_transitionwise(case, ora, knobs=None, device="cuda:0", callback=None):
+def gpu_run_transitionwise(case, ora, knobs=None, device="cuda:0", callback=None, target=None):
     """Transition-level protocol: before EVERY transition the device state of every chain is set to
     the oracle's state before that transition, so both sides see identical (q0, var, step-size state, Welford state,
     normals, uniform tape) and only one transition's arithmetic is compared -- differences cannot compound through
@@ -210,7 +210,7 @@ def gpu_run_transitionwise(case, ora, knobs=None, device="cuda:0", callback=None
     normals, uniforms, _ = ora["tapes"]
     Cn, T, D = normals.shape
     ch = gpu_chains(case, Cn, device)
-    tgt, params = gpu_target(case), gpu_params(case)
+    tgt, params = target or gpu_target(case), gpu_params(case)
     dev = ch.device
     up = lambda x: torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float64, device=dev)  # noqa: E731
     pre = {k: up(v) for k, v in ora["pre"].items()}
@@ -237,7 +237,7 @@ def gpu_run_transitionwise(case, ora, knobs=None, device="cuda:0", callback=None
 
 
 def run_case_on_gpu_and_oracle(name, n_trans=None, knobs=None, device="cuda:0", chained=False,
-                               chunks=1, callback=None, overrides=None) -> ParityResult:
+                               chunks=1, callback=None, overrides=None, target=None) -> ParityResult:
     """`callback`: None = fused kernels; "torch" / "torch-graph" / "torch-replay" = callback mode with the case's density
     as a batched torch op (eager host loop / device-driven WHILE graph / replayed graphs); "numpy" = callback mode with
     the oracle's per-chain NumPy callable."""
@@ -255,14 +255,15 @@ def run_case_on_gpu_and_oracle(name, n_trans=None, knobs=None, device="cuda:0", 
         callback = gc.target_fn(case)()
     if chained:
         trace, st, ch = gpu_run_chained(case, ora["tapes"], chunks=chunks, knobs=knobs, device=device,
-                                        callback=callback)
+                                        callback=callback, target=target)
         q, var, wel, ad = _read_state(ch)
         # only the final adaptation state is observable in a chained run
         return ParityResult(str(case["kind"]), trace, ora["trace"], {n: st[:, :, i] for n, i in table.items()},
                             ora["stats"], var[:, None], ora["post"]["var"][:, -1:], ad[:, None],
                             ora["post"]["adapt"][:, -1:], wel[:, None], ora["post"]["welford"][:, -1:],
                             st[:, :, L.STAT_N_UNIFORMS], ora["tapes"][2], ch.status.cpu().numpy())
-    q, var, wel, ad, st, ch = gpu_run_transitionwise(case, ora, knobs=knobs, device=device, callback=callback)
+    q, var, wel, ad, st, ch = gpu_run_transitionwise(case, ora, knobs=knobs, device=device, callback=callback,
+                                                     target=target)
     return ParityResult(str(case["kind"]), q, ora["trace"], {n: st[:, :, i] for n, i in table.items()}, ora["stats"],
                         var, ora["post"]["var"], ad, ora["post"]["adapt"], wel, ora["post"]["welford"],
                         st[:, :, L.STAT_N_UNIFORMS], ora["tapes"][2], ch.status.cpu().numpy())
