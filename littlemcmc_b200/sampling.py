@@ -190,6 +190,9 @@ def sample(logp_dlogp_func, model_ndim, draws=1000, tune=1000, step=None, init="
     stats_dev = torch.cat(stats_blocks, 1) if len(stats_blocks) > 1 else stats_blocks[0]
     stats_dev = stats_dev[:, :done]                     # an interrupted block's statistics are dropped with its draws
     step._account(stats_dev, min(int(tune), done))
+    # leapfrogs of the WHOLE run (tuning included, whatever is shipped): BASELINE.json's metric counts them all
+    count_col = step._stat_columns.get("tree_size", step._stat_columns.get("n_steps"))
+    step._last_run_leapfrogs = float(stats_dev[:, :, count_col].sum().item()) if stats_dev.numel() else 0.0
 
     _mark("account")
     stats_kept = stats_dev[:, keep_from:]

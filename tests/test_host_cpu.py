@@ -165,7 +165,8 @@ def test_arviz_export_dicts():
 
 def test_bench_reference_arm_prints_the_contract_line():
     """`bench.py --impl reference` (the CPU arm the driver runs next to the GPU arm): one JSON line with the contract's
-    keys, the oracle port timed on the host cores, zero transfer bytes."""
+    keys, the unmodified reference (oracle/_ref, when built: this container) or else its oracle port timed on the host
+    cores, zero transfer bytes, and the same `config` the GPU arm prints."""
     import json
     import subprocess
     import sys
@@ -179,7 +180,12 @@ def test_bench_reference_arm_prints_the_contract_line():
                 "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
         assert key in line, key
     assert line["impl"] == "reference" and line["metric"].startswith("leapfrog-steps/sec") and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
+    have_ref = os.path.exists(os.path.join(root, "oracle", "_ref", "littlemcmc", "__init__.py"))
+    assert line["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")
+    assert line["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
+    sys.path.insert(0, root)
+    import bench
+    assert line["config"] == bench.static_config("cfg2", 1)      # identical to the GPU arm's description of the workload
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["e2e"]["value"] == line["value"] and line["config"]["workload"].startswith("cfg2")
     # ranks other than 0 print nothing and exit 0 (torchrun launches the arm on every rank)
