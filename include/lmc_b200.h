@@ -33,7 +33,7 @@ typedef unsigned long uintptr_t;
 extern "C" {
 #endif
 
-#define LMC_ABI_VERSION 2
+#define LMC_ABI_VERSION 3
 
 #define LMC_OK 0
 #define LMC_ERR_BADARG (-1)      /* null pointer, bad size/stride/alignment */
@@ -172,6 +172,20 @@ typedef struct lmc_sampler_args {
   int32_t tune_smem_vecs; /* -1 = library picks how many scratch vectors live in shared memory; else force  */
   int32_t tune_max_slots; /* 0 = library picks the number of resident chain slots; else cap it              */
   int32_t tune_chunk;  /* chunked warp kernel: leaves per chunk (2, 4, 8, 16); 0 = library picks            */
+
+  /* One launch for a whole run with a host-resident trace (ABI v3; fused and user-target kernels only, the callback and
+   * dense state machines require 0 / NULL).  The reference discards tuning draws after the fact (sampling.py:473-476)
+   * and fills its trace draw by draw (:513); here
+   *   trace_skip      the first `trace_skip` transitions of the call are not kept: transition t writes trace row
+   *                   max(t - trace_skip, 0) (a discarded draw lands on row 0 and is overwritten by the first kept one),
+   *                   so `trace` holds n_trans - trace_skip rows per chain; statistics are written for every transition;
+   *   progress        device counters, one per block of `progress_block` KEPT draws (zeroed by the caller): a chain
+   *                   adds 1 to counter b after its kept draw (b + 1) * progress_block - 1 (or its last one) is
+   *                   globally visible.  counter b == n_chains  <=>  rows [b * progress_block, (b + 1) * progress_block)
+   *                   of every chain are final: the caller's copy engine can ship them while the launch keeps sampling. */
+  int32_t trace_skip;
+  int32_t progress_block;
+  int32_t* progress;
 } lmc_sampler_args;
 
 /* Library / ABI version (LMC_ABI_VERSION of the build). */

@@ -6,7 +6,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("LMC_LIB_PATH") or os.path.join(_HERE, "liblmc_b200.so")  # env: kernel experiments only
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 OK, ERR_BADARG, ERR_UNSUPPORTED, ERR_LAUNCH, ERR_WORKSPACE = 0, -1, -2, -3, -4
 TARGET_DIAG_GAUSSIAN, TARGET_FUNNEL = 0, 1
 RNG_TAPE, RNG_PHILOX = 0, 1
@@ -50,6 +50,7 @@ class SamplerArgs(C.Structure):
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("stream", C.c_void_p),
         ("tune_group", C.c_int32), ("tune_smem_vecs", C.c_int32), ("tune_max_slots", C.c_int32),
         ("tune_chunk", C.c_int32),
+        ("trace_skip", C.c_int32), ("progress_block", C.c_int32), ("progress", C.c_void_p),
     ]
 
 

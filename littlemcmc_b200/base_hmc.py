@@ -87,7 +87,8 @@ class BaseHMC:
                     target_accept=sa._target, gamma=sa._gamma, k=sa._k, t0=sa._t0, Emax=self.Emax)
 
     # ---- batched driver entry ----------------------------------------------------------------------------------------
-    def _run(self, n_trans, n_tune, tapes=None, trace=None, stats=None, events=None):
+    def _run(self, n_trans, n_tune, tapes=None, trace=None, stats=None, events=None, trace_skip=0, progress=None,
+             progress_block=0):
         """`n_trans` transitions of every chain starting at `self.iter_count`; transitions with index < `n_tune` tune.
         Returns device tensors (trace [C, n_trans, D], stats [C, n_trans, NSTATS]).
 
@@ -118,7 +119,9 @@ class BaseHMC:
             if events is not None:
                 events[1].record()
         elif fused is not None:
-            tr, st = engine.run_transitions(self._kind, self._chains, fused, knobs=self._knobs, events=events, **common)
+            tr, st = engine.run_transitions(self._kind, self._chains, fused, knobs=self._knobs, events=events,
+                                            trace_skip=trace_skip, progress=progress, progress_block=progress_block,
+                                            **common)
         else:
             graph = getattr(self._logp_dlogp_func, "cuda_graph", False)
             if events is not None:

@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(cb_block<G>()) cb_advance_kernel(const lmc_cal
         s.i = 0;
         s.dir = 1;
 #pragma unroll
-        for (int k = 0; k < NP; ++k) sc.vec(V_Q0)[k * G] = q[k];
+        for (int k = 0; k < NP; ++k) sc.st(V_Q0, k, q[k]);
       }
     }
   } else {
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(cb_block<G>()) cb_advance_kernel(const lmc_cal
     double k1[1] = {0.0};
 #pragma unroll
     for (int k = 0; k < NP; ++k) {
-      p[k] = axpy2(sc.vec(V_P)[k * G], dt, g[k]);
+      p[k] = axpy2(sc.ld(V_P, k), dt, g[k]);
       k1[0] = dot2(k1[0], p[k], mul2(var[k], p[k]));
     }
     grp.allreduce(k1);
@@ -210,9 +210,9 @@ __global__ void __launch_bounds__(cb_block<G>()) cb_advance_kernel(const lmc_cal
           const int base = (s.dir > 0 ? T_RQ : T_LQ);  // self.right / self.left = tree.right (:304 / :313)
 #pragma unroll
           for (int k = 0; k < NP; ++k) {
-            sc.vec(tvid(tail, base + 0))[k * G] = q[k];
-            sc.vec(tvid(tail, base + 1))[k * G] = p[k];
-            sc.vec(tvid(tail, base + 2))[k * G] = g[k];
+            sc.st(tvid(tail, base + 0), k, q[k]);
+            sc.st(tvid(tail, base + 1), k, p[k]);
+            sc.st(tvid(tail, base + 2), k, g[k]);
           }
           s.last_dir = s.dir;
           ++s.d;
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(cb_block<G>()) cb_advance_kernel(const lmc_cal
         if (!diverging) accepted = !(next_uniform() >= accept_stat);
         if (!accepted) {
 #pragma unroll
-          for (int k = 0; k < NP; ++k) q[k] = sc.vec(V_Q0)[k * G];
+          for (int k = 0; k < NP; ++k) q[k] = sc.ld(V_Q0, k);
         }
         stat_a = (double)s.n_steps;
         stat_b = s.path_length;
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(cb_block<G>()) cb_advance_kernel(const lmc_cal
       stat_c = s.tr.max_dE;
       stat_logp = s.tr.prop_logp;
 #pragma unroll
-      for (int k = 0; k < NP; ++k) q[k] = sc.vec(tvid(tail, T_PROPQ))[k * G];  // hmc_step.end.q
+      for (int k = 0; k < NP; ++k) q[k] = sc.ld(tvid(tail, T_PROPQ), k);  // hmc_step.end.q
     }
   }
 
@@ -324,9 +324,9 @@ __global__ void __launch_bounds__(cb_block<G>()) cb_advance_kernel(const lmc_cal
         const int base = (s.dir > 0 ? T_RQ : T_LQ);
 #pragma unroll
         for (int k = 0; k < NP; ++k) {
-          q[k] = sc.vec(tvid(tail, base + 0))[k * G];
-          p[k] = sc.vec(tvid(tail, base + 1))[k * G];
-          g[k] = sc.vec(tvid(tail, base + 2))[k * G];
+          q[k] = sc.ld(tvid(tail, base + 0), k);
+          p[k] = sc.ld(tvid(tail, base + 1), k);
+          g[k] = sc.ld(tvid(tail, base + 2), k);
         }
       }
       s.i = 0;
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(cb_block<G>()) cb_advance_kernel(const lmc_cal
     for (int k = 0; k < NP; ++k) {
       p[k] = axpy2(p[k], dt, g[k]);
       q[k] = axpy2(q[k], e, mul2(var[k], p[k]));
-      sc.vec(V_P)[k * G] = p[k];
+      sc.st(V_P, k, p[k]);
     }
     store_row<G, NP>(c.q_eval + off, lane, ldh, q);
     s.phase = PH_LEAF;
@@ -396,6 +396,7 @@ static int cb_check(int kind, const lmc_callback_args* c, int* G, int* NP, size_
   } else if (a.max_steps < 1) {
     return LMC_ERR_BADARG;
   }
+  if (a.trace_skip != 0 || a.progress) return LMC_ERR_UNSUPPORTED;  // single-launch host traces: fused kernels only
   if (!cb_pick_shape(a.ndim, G, NP)) return LMC_ERR_UNSUPPORTED;
   *n_vecs = cb_vecs(kind, scratch_depth(a));
   *vec_off = (size_t)a.n_chains * kMachineBytes;

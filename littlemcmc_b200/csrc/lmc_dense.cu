@@ -106,11 +106,11 @@ __device__ __forceinline__ bool dn_merge_level(const Scratch<G, NP>& sc, Group<G
   double2 t1_lp[NP], t1_lv[NP], t1_rp[NP], t1_rv[NP], t1_ps[NP];
 #pragma unroll
   for (int k = 0; k < NP; ++k) {
-    t1_lp[k] = sc.vec(dv_stack(lvl, S_LP))[k * G];
-    t1_lv[k] = sc.vec(dv_stack(lvl, S_LV))[k * G];
-    t1_rp[k] = sc.vec(dv_stack(lvl, S_RP))[k * G];
-    t1_rv[k] = sc.vec(dv_stack(lvl, S_RV))[k * G];
-    t1_ps[k] = sc.vec(dv_stack(lvl, S_PS))[k * G];
+    t1_lp[k] = sc.ld(dv_stack(lvl, S_LP), k);
+    t1_lv[k] = sc.ld(dv_stack(lvl, S_LV), k);
+    t1_rp[k] = sc.ld(dv_stack(lvl, S_RP), k);
+    t1_rv[k] = sc.ld(dv_stack(lvl, S_RV), k);
+    t1_ps[k] = sc.ld(dv_stack(lvl, S_PS), k);
   }
   bool turn;
   if (lvl == 0) {
@@ -172,15 +172,15 @@ __device__ __forceinline__ void dn_push_cur(const Scratch<G, NP>& sc, StackScala
     cur.pslot = __ffs(free_slots) - 1;
     free_slots &= ~(1u << cur.pslot);
 #pragma unroll
-    for (int k = 0; k < NP; ++k) sc.vec(dv_prop(max_depth, cur.pslot))[k * G] = q[k];
+    for (int k = 0; k < NP; ++k) sc.st(dv_prop(max_depth, cur.pslot), k, q[k]);
   }
 #pragma unroll
   for (int k = 0; k < NP; ++k) {
-    sc.vec(dv_stack(lvl, S_LP))[k * G] = cur_lp[k];
-    sc.vec(dv_stack(lvl, S_LV))[k * G] = cur_lv[k];
-    sc.vec(dv_stack(lvl, S_RP))[k * G] = p[k];
-    sc.vec(dv_stack(lvl, S_RV))[k * G] = v[k];
-    sc.vec(dv_stack(lvl, S_PS))[k * G] = cur_ps[k];
+    sc.st(dv_stack(lvl, S_LP), k, cur_lp[k]);
+    sc.st(dv_stack(lvl, S_LV), k, cur_lv[k]);
+    sc.st(dv_stack(lvl, S_RP), k, p[k]);
+    sc.st(dv_stack(lvl, S_RV), k, v[k]);
+    sc.st(dv_stack(lvl, S_PS), k, cur_ps[k]);
   }
   if (sc.lane == 0) {
     ss->wm[lvl] = cur.w.m;
@@ -203,10 +203,10 @@ __device__ __forceinline__ bool dn_extend_top(const Scratch<G, NP>& sc, Group<G>
     tr.prop_logp = cur.plogp;
     if (cur.pslot == kLeafProp) {
 #pragma unroll
-      for (int k = 0; k < NP; ++k) sc.vec(tail + DT_PROPQ)[k * G] = q[k];
+      for (int k = 0; k < NP; ++k) sc.st(tail + DT_PROPQ, k, q[k]);
     } else {
 #pragma unroll
-      for (int k = 0; k < NP; ++k) sc.vec(tail + DT_PROPQ)[k * G] = sc.vec(dv_prop(max_depth, cur.pslot))[k * G];
+      for (int k = 0; k < NP; ++k) sc.st(tail + DT_PROPQ, k, sc.ld(dv_prop(max_depth, cur.pslot), k));
     }
   }
   tr.Wp = xf_add(tr.Wp, cur.w);    // :325
@@ -214,10 +214,10 @@ __device__ __forceinline__ bool dn_extend_top(const Scratch<G, NP>& sc, Group<G>
   double d6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
   for (int k = 0; k < NP; ++k) {
-    const double2 psum = add2(sc.vec(tail + DT_PSUM)[k * G], cur_ps[k]);  // self.p_sum[:] += tree.p_sum (:329)
-    sc.vec(tail + DT_PSUM)[k * G] = psum;
-    const double2 oLp = sc.vec(tail + DT_LP)[k * G], oRp = sc.vec(tail + DT_RP)[k * G];
-    const double2 voL = sc.vec(tail + DT_LV)[k * G], voR = sc.vec(tail + DT_RV)[k * G];
+    const double2 psum = add2(sc.ld(tail + DT_PSUM, k), cur_ps[k]);  // self.p_sum[:] += tree.p_sum (:329)
+    sc.st(tail + DT_PSUM, k, psum);
+    const double2 oLp = sc.ld(tail + DT_LP, k), oRp = sc.ld(tail + DT_RP, k);
+    const double2 voL = sc.ld(tail + DT_LV, k), voR = sc.ld(tail + DT_RV, k);
     const double2 vTl = cur_lv[k], vTr = v[k];
     if (dir > 0) {  // (:300-303, :333-339, with the aliased p_sum)
       const double2 ps1 = add2(psum, cur_lp[k]);
@@ -374,18 +374,18 @@ __global__ void __launch_bounds__(dn_block<G>()) dn_advance_kernel(const lmc_den
         s.last_dir = 0;
 #pragma unroll
         for (int k = 0; k < NP; ++k) {  // _Tree.__init__ (nuts.py:267-282)
-          sc.vec(tail + DT_LQ)[k * G] = q[k];
-          sc.vec(tail + DT_LP)[k * G] = p[k];
-          sc.vec(tail + DT_LG)[k * G] = g[k];
-          sc.vec(tail + DT_LV)[k * G] = v[k];
-          sc.vec(tail + DT_LW)[k * G] = w[k];
-          sc.vec(tail + DT_RQ)[k * G] = q[k];
-          sc.vec(tail + DT_RP)[k * G] = p[k];
-          sc.vec(tail + DT_RG)[k * G] = g[k];
-          sc.vec(tail + DT_RV)[k * G] = v[k];
-          sc.vec(tail + DT_RW)[k * G] = w[k];
-          sc.vec(tail + DT_PSUM)[k * G] = p[k];
-          sc.vec(tail + DT_PROPQ)[k * G] = q[k];
+          sc.st(tail + DT_LQ, k, q[k]);
+          sc.st(tail + DT_LP, k, p[k]);
+          sc.st(tail + DT_LG, k, g[k]);
+          sc.st(tail + DT_LV, k, v[k]);
+          sc.st(tail + DT_LW, k, w[k]);
+          sc.st(tail + DT_RQ, k, q[k]);
+          sc.st(tail + DT_RP, k, p[k]);
+          sc.st(tail + DT_RG, k, g[k]);
+          sc.st(tail + DT_RV, k, v[k]);
+          sc.st(tail + DT_RW, k, w[k]);
+          sc.st(tail + DT_PSUM, k, p[k]);
+          sc.st(tail + DT_PROPQ, k, q[k]);
         }
         new_doubling = s.max_depth > 0;
         trans_end = !new_doubling;
@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(dn_block<G>()) dn_advance_kernel(const lmc_den
         s.i = 0;
         s.dir = 1;
 #pragma unroll
-        for (int k = 0; k < NP; ++k) sc.vec(V_Q0)[k * G] = q[k];
+        for (int k = 0; k < NP; ++k) sc.st(V_Q0, k, q[k]);
       }
     }
   } else {  // DPH_LEAF_V
@@ -441,11 +441,11 @@ __global__ void __launch_bounds__(dn_block<G>()) dn_advance_kernel(const lmc_den
           const int base = tail + (s.dir > 0 ? DT_RQ : DT_LQ);  // self.right / self.left = tree.right (:304 / :313)
 #pragma unroll
           for (int k = 0; k < NP; ++k) {
-            sc.vec(base + 0)[k * G] = q[k];
-            sc.vec(base + 1)[k * G] = p[k];
-            sc.vec(base + 2)[k * G] = g[k];
-            sc.vec(base + 3)[k * G] = v[k];
-            sc.vec(base + 4)[k * G] = w[k];
+            sc.st(base + 0, k, q[k]);
+            sc.st(base + 1, k, p[k]);
+            sc.st(base + 2, k, g[k]);
+            sc.st(base + 3, k, v[k]);
+            sc.st(base + 4, k, w[k]);
           }
           s.last_dir = s.dir;
           ++s.d;
@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(dn_block<G>()) dn_advance_kernel(const lmc_den
         if (!diverging) accepted = !(next_uniform() >= accept_stat);
         if (!accepted) {
 #pragma unroll
-          for (int k = 0; k < NP; ++k) q[k] = sc.vec(V_Q0)[k * G];
+          for (int k = 0; k < NP; ++k) q[k] = sc.ld(V_Q0, k);
         }
         stat_a = (double)s.n_steps;
         stat_b = s.path_length;
@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(dn_block<G>()) dn_advance_kernel(const lmc_den
       stat_c = s.tr.max_dE;
       stat_logp = s.tr.prop_logp;
 #pragma unroll
-      for (int k = 0; k < NP; ++k) q[k] = sc.vec(tail + DT_PROPQ)[k * G];  // hmc_step.end.q
+      for (int k = 0; k < NP; ++k) q[k] = sc.ld(tail + DT_PROPQ, k);  // hmc_step.end.q
     }
   }
 
@@ -553,11 +553,11 @@ __global__ void __launch_bounds__(dn_block<G>()) dn_advance_kernel(const lmc_den
         const int base = tail + (s.dir > 0 ? DT_RQ : DT_LQ);
 #pragma unroll
         for (int k = 0; k < NP; ++k) {
-          q[k] = sc.vec(base + 0)[k * G];
-          p[k] = sc.vec(base + 1)[k * G];
-          g[k] = sc.vec(base + 2)[k * G];
-          v[k] = sc.vec(base + 3)[k * G];
-          w[k] = sc.vec(base + 4)[k * G];
+          q[k] = sc.ld(base + 0, k);
+          p[k] = sc.ld(base + 1, k);
+          g[k] = sc.ld(base + 2, k);
+          v[k] = sc.ld(base + 3, k);
+          w[k] = sc.ld(base + 4, k);
         }
       }
       s.i = 0;
@@ -629,6 +629,7 @@ static int dn_check(int kind, const lmc_dense_args* c, int* G, int* NP, size_t* 
   } else if (a.max_steps < 1) {
     return LMC_ERR_BADARG;
   }
+  if (a.trace_skip != 0 || a.progress) return LMC_ERR_UNSUPPORTED;  // single-launch host traces: fused kernels only
   if (!dn_pick_shape(a.ndim, G, NP)) return LMC_ERR_UNSUPPORTED;
   *n_vecs = dn_vecs(kind, scratch_depth(a));
   *vec_off = (size_t)a.n_chains * kDnMachineBytes;

@@ -23,6 +23,8 @@ int check_sampler_args(const lmc_sampler_args* a, int kind, bool check_target) {
   } else {
     return LMC_ERR_BADARG;
   }
+  if (a->trace_skip < 0 || a->trace_skip > a->n_trans) return LMC_ERR_BADARG;
+  if (a->progress && a->progress_block < 1) return LMC_ERR_BADARG;
   if (kind == KIND_NUTS) {
     if (a->tune_chunk != 0 && a->tune_chunk != 2 && a->tune_chunk != 4 && a->tune_chunk != 8 && a->tune_chunk != 16)
       return LMC_ERR_BADARG;

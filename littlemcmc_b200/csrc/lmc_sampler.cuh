@@ -59,6 +59,17 @@ __host__ __device__ inline SchedView sched_view(void* workspace, int n_chains) {
 }
 constexpr unsigned kDeadBit = 0x80000000u;
 
+// lmc_sampler_args.progress: after transition t of a chain is globally visible (the caller fenced), one thread of the
+// group reports the kept-draw block it completes, if any
+__device__ __forceinline__ bool completes_block(const lmc_sampler_args& a, int t) {
+  if (!a.progress || t < a.trace_skip) return false;
+  const int kept = t - a.trace_skip + 1;  // kept draws of this chain so far
+  return kept % a.progress_block == 0 || t + 1 == a.n_trans;
+}
+__device__ __forceinline__ void report_block(const lmc_sampler_args& a, int t) {
+  atomicAdd(a.progress + (t - a.trace_skip) / a.progress_block, 1);
+}
+
 static __global__ void sched_init_kernel(void* workspace, int n_chains) {
   const SchedView sv = sched_view(workspace, n_chains);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -165,7 +176,8 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
     // output rows of this unit: computed where they are written (epilogue / dead-chain fill), not held across the tree
     auto stats_row = [&]() -> double* { return a.stats + row * LMC_NSTATS; };
     auto trace_row = [&]() -> double* {
-      return a.trace + (size_t)chain * a.trace_chain_stride + (size_t)t * a.trace_draw_stride;
+      return a.trace + (size_t)chain * a.trace_chain_stride +
+             (size_t)(t > a.trace_skip ? t - a.trace_skip : 0) * a.trace_draw_stride;
     };
     int status = 0;
 
@@ -236,9 +248,9 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
               const int base = (dir > 0 ? T_RQ : T_LQ);
 #pragma unroll
               for (int k = 0; k < NP; ++k) {
-                q[k] = sc.vec(tvid(tail, base + 0))[k * G];
-                p[k] = sc.vec(tvid(tail, base + 1))[k * G];
-                g[k] = sc.vec(tvid(tail, base + 2))[k * G];
+                q[k] = sc.ld(tvid(tail, base + 0), k);
+                p[k] = sc.ld(tvid(tail, base + 1), k);
+                g[k] = sc.ld(tvid(tail, base + 2), k);
               }
             }
             const double eps_d = dir > 0 ? eps : -eps;
@@ -306,9 +318,9 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
               const int base = (dir > 0 ? T_RQ : T_LQ);
 #pragma unroll
               for (int k = 0; k < NP; ++k) {
-                sc.vec(tvid(tail, base + 0))[k * G] = q[k];
-                sc.vec(tvid(tail, base + 1))[k * G] = p[k];
-                sc.vec(tvid(tail, base + 2))[k * G] = g[k];
+                sc.st(tvid(tail, base + 0), k, q[k]);
+                sc.st(tvid(tail, base + 1), k, p[k]);
+                sc.st(tvid(tail, base + 2), k, g[k]);
               }
               reg_edge = dir;
             } else {
@@ -324,7 +336,7 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
           stat_c = tr.max_dE;
           stat_logp = tr.prop_logp;
 #pragma unroll
-          for (int k = 0; k < NP; ++k) q[k] = sc.vec(tvid(tail, T_PROPQ))[k * G];  // hmc_step.end.q
+          for (int k = 0; k < NP; ++k) q[k] = sc.ld(tvid(tail, T_PROPQ), k);  // hmc_step.end.q
         } else {
           // ---- HamiltonianMC._hamiltonian_step (hmc.py:140-182) -------------------------------------------------
           double2 q0[NP];
@@ -419,6 +431,7 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
     // ---- push the chain back for its next transition ---------------------------------------------------------------
     __threadfence();  // release: this thread's state writes become visible before the push below
     group_barrier<G>();
+    if (lane == 0 && completes_block(a, t)) report_block(a, t);
     if (lane == 0 && t + 1 < a.n_trans) {
       sv.prog[chain] = t + 1;
       __threadfence();

@@ -98,7 +98,8 @@ __global__ void __launch_bounds__(G, MINCTAS) sampler_lean_kernel(const lmc_samp
     // output rows of this unit: computed where they are written (epilogue / dead-chain fill), not held across the tree
     auto stats_row = [&]() -> double* { return a.stats + row * LMC_NSTATS; };
     auto trace_row = [&]() -> double* {
-      return a.trace + (size_t)chain * a.trace_chain_stride + (size_t)t * a.trace_draw_stride;
+      return a.trace + (size_t)chain * a.trace_chain_stride +
+             (size_t)(t > a.trace_skip ? t - a.trace_skip : 0) * a.trace_draw_stride;
     };
     int status = 0;
 
@@ -180,9 +181,9 @@ __global__ void __launch_bounds__(G, MINCTAS) sampler_lean_kernel(const lmc_samp
             const int base = (dir > 0 ? T_RQ : T_LQ);
 #pragma unroll
             for (int k = 0; k < NP; ++k) {
-              q[k] = sc.vec(tvid(tail, base + 0))[k * G];
-              p[k] = sc.vec(tvid(tail, base + 1))[k * G];
-              g[k] = sc.vec(tvid(tail, base + 2))[k * G];
+              q[k] = sc.ld(tvid(tail, base + 0), k);
+              p[k] = sc.ld(tvid(tail, base + 1), k);
+              g[k] = sc.ld(tvid(tail, base + 2), k);
             }
           }
           const double eps_d = dir > 0 ? eps : -eps;
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(G, MINCTAS) sampler_lean_kernel(const lmc_samp
               double d2[2] = {0.0, 0.0};
 #pragma unroll
               for (int k = 0; k < NP; ++k) {
-                const double2 t1p = sc.vec(vid_stack(0, 0))[k * G];
+                const double2 t1p = sc.ld(vid_stack(0, 0), k);
                 const double2 vk = s_var[k * G];
                 const double2 ps = add2(t1p, p[k]);
                 d2[0] = dot2(d2[0], ps, mul2(vk, t1p));
@@ -251,10 +252,10 @@ __global__ void __launch_bounds__(G, MINCTAS) sampler_lean_kernel(const lmc_samp
               double d6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
               for (int k = 0; k < NP; ++k) {
-                const double2 t1_lp = sc.vec(vid_stack(lvl, 0))[k * G];
-                const double2 t1_rp = sc.vec(vid_stack(lvl, 1))[k * G];
-                const double2 t1_ps = sc.vec(vid_stack(lvl, 2))[k * G];
-                const double2 c_lp = sc.vec(cur_lp_id)[k * G];
+                const double2 t1_lp = sc.ld(vid_stack(lvl, 0), k);
+                const double2 t1_rp = sc.ld(vid_stack(lvl, 1), k);
+                const double2 t1_ps = sc.ld(vid_stack(lvl, 2), k);
+                const double2 c_lp = sc.ld(cur_lp_id, k);
                 const double2 c_ps = s_cps[k * G];
                 const double2 vk = s_var[k * G];
                 const double2 ps = add2(t1_ps, c_ps);   // :390
@@ -300,13 +301,13 @@ __global__ void __launch_bounds__(G, MINCTAS) sampler_lean_kernel(const lmc_samp
                 cur.pslot = __ffs(free_slots) - 1;
                 free_slots &= ~(1u << cur.pslot);
 #pragma unroll
-                for (int k = 0; k < NP; ++k) sc.vec(vid_prop(cur.pslot))[k * G] = q[k];
+                for (int k = 0; k < NP; ++k) sc.st(vid_prop(cur.pslot), k, q[k]);
               }
 #pragma unroll
               for (int k = 0; k < NP; ++k) {
-                sc.vec(vid_stack(lvl, 0))[k * G] = sc.vec(cur_lp_id)[k * G];
-                sc.vec(vid_stack(lvl, 1))[k * G] = p[k];
-                sc.vec(vid_stack(lvl, 2))[k * G] = s_cps[k * G];
+                sc.st(vid_stack(lvl, 0), k, sc.ld(cur_lp_id, k));
+                sc.st(vid_stack(lvl, 1), k, p[k]);
+                sc.st(vid_stack(lvl, 2), k, s_cps[k * G]);
               }
               if (lane == 0) {
                 ss->wm[lvl] = cur.w.m;
@@ -333,10 +334,10 @@ __global__ void __launch_bounds__(G, MINCTAS) sampler_lean_kernel(const lmc_samp
               tr.prop_logp = cur.plogp;
               if (cur.pslot == kLeafProp) {
 #pragma unroll
-                for (int k = 0; k < NP; ++k) sc.vec(tvid(tail, T_PROPQ))[k * G] = q[k];
+                for (int k = 0; k < NP; ++k) sc.st(tvid(tail, T_PROPQ), k, q[k]);
               } else {
 #pragma unroll
-                for (int k = 0; k < NP; ++k) sc.vec(tvid(tail, T_PROPQ))[k * G] = sc.vec(vid_prop(cur.pslot))[k * G];
+                for (int k = 0; k < NP; ++k) sc.st(tvid(tail, T_PROPQ), k, sc.ld(vid_prop(cur.pslot), k));
               }
             }
             tr.Wp = xf_add(tr.Wp, cur.w);
@@ -346,11 +347,11 @@ __global__ void __launch_bounds__(G, MINCTAS) sampler_lean_kernel(const lmc_samp
 #pragma unroll
             for (int k = 0; k < NP; ++k) {
               const double2 c_ps = single ? p[k] : s_cps[k * G];
-              const double2 c_lp = single ? p[k] : sc.vec(cur_lp_id)[k * G];
+              const double2 c_lp = single ? p[k] : sc.ld(cur_lp_id, k);
               const double2 vk = s_var[k * G];
-              const double2 psum = add2(sc.vec(tvid(tail, T_PSUM))[k * G], c_ps);  // :329
-              sc.vec(tvid(tail, T_PSUM))[k * G] = psum;
-              const double2 oLp = sc.vec(tvid(tail, T_LP))[k * G], oRp = sc.vec(tvid(tail, T_RP))[k * G];
+              const double2 psum = add2(sc.ld(tvid(tail, T_PSUM), k), c_ps);  // :329
+              sc.st(tvid(tail, T_PSUM), k, psum);
+              const double2 oLp = sc.ld(tvid(tail, T_LP), k), oRp = sc.ld(tvid(tail, T_RP), k);
               const double2 voL = mul2(vk, oLp), voR = mul2(vk, oRp);
               const double2 vTl = mul2(vk, c_lp), vTr = mul2(vk, p[k]);
               if (dir > 0) {
@@ -380,9 +381,9 @@ __global__ void __launch_bounds__(G, MINCTAS) sampler_lean_kernel(const lmc_samp
             const int base = (dir > 0 ? T_RQ : T_LQ);
 #pragma unroll
             for (int k = 0; k < NP; ++k) {
-              sc.vec(tvid(tail, base + 0))[k * G] = q[k];
-              sc.vec(tvid(tail, base + 1))[k * G] = p[k];
-              sc.vec(tvid(tail, base + 2))[k * G] = g[k];
+              sc.st(tvid(tail, base + 0), k, q[k]);
+              sc.st(tvid(tail, base + 1), k, p[k]);
+              sc.st(tvid(tail, base + 2), k, g[k]);
             }
             reg_edge = dir;
           } else {
@@ -391,7 +392,7 @@ __global__ void __launch_bounds__(G, MINCTAS) sampler_lean_kernel(const lmc_samp
         }
         const double accept_stat = mean_tree_accept(tr);
 #pragma unroll
-        for (int k = 0; k < NP; ++k) q[k] = sc.vec(tvid(tail, T_PROPQ))[k * G];  // hmc_step.end.q
+        for (int k = 0; k < NP; ++k) q[k] = sc.ld(tvid(tail, T_PROPQ), k);  // hmc_step.end.q
 
         double* const ad = a.adapt + (size_t)chain * LMC_ADAPT_STRIDE;
         DualAvg da{__ldcg(ad + LMC_ADAPT_LOG_STEP), __ldcg(ad + LMC_ADAPT_LOG_BAR), __ldcg(ad + LMC_ADAPT_HBAR),
@@ -457,6 +458,7 @@ __global__ void __launch_bounds__(G, MINCTAS) sampler_lean_kernel(const lmc_samp
     }
     __threadfence();
     __syncthreads();
+    if (lane == 0 && completes_block(a, t)) report_block(a, t);
     if (lane == 0 && t + 1 < a.n_trans) {
       sv.prog[chain] = t + 1;
       __threadfence();

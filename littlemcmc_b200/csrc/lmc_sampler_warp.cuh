@@ -156,7 +156,8 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
     const size_t row = (size_t)chain * a.n_trans + t;
     auto stats_row = [&]() -> double* { return a.stats + row * LMC_NSTATS; };
     auto trace_row = [&]() -> double* {
-      return a.trace + (size_t)chain * a.trace_chain_stride + (size_t)t * a.trace_draw_stride;
+      return a.trace + (size_t)chain * a.trace_chain_stride +
+             (size_t)(t > a.trace_skip ? t - a.trace_skip : 0) * a.trace_draw_stride;
     };
     int status = 0;
 
@@ -249,9 +250,9 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
             const int eb = (dir > 0 ? T_RQ : T_LQ);
 #pragma unroll
             for (int k = 0; k < NP; ++k) {
-              q[k] = sc.vec(tvid(tail, eb + 0))[k * G];
-              p[k] = sc.vec(tvid(tail, eb + 1))[k * G];
-              g[k] = sc.vec(tvid(tail, eb + 2))[k * G];
+              q[k] = sc.ld(tvid(tail, eb + 0), k);
+              p[k] = sc.ld(tvid(tail, eb + 1), k);
+              g[k] = sc.ld(tvid(tail, eb + 2), k);
             }
           }
           const double eps_d = dir > 0 ? eps : -eps;
@@ -474,13 +475,13 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
                   free_slots &= ~(1u << cur.pslot);
 #pragma unroll
                   for (int k = 0; k < NP; ++k)
-                    sc.vec(vid_prop(cur.pslot))[k * G] = ring_q[(size_t)(pidx * NP + k) * 32];
+                    sc.st(vid_prop(cur.pslot), k, ring_q[(size_t)(pidx * NP + k) * 32]);
                 }
 #pragma unroll
                 for (int k = 0; k < NP; ++k) {
-                  sc.vec(vid_stack(lvl, 0))[k * G] = cur_lp[k];
-                  sc.vec(vid_stack(lvl, 1))[k * G] = p[k];
-                  sc.vec(vid_stack(lvl, 2))[k * G] = cur_ps[k];
+                  sc.st(vid_stack(lvl, 0), k, cur_lp[k]);
+                  sc.st(vid_stack(lvl, 1), k, p[k]);
+                  sc.st(vid_stack(lvl, 2), k, cur_ps[k]);
                 }
                 __syncwarp();
                 if (lane == 0) {
@@ -530,9 +531,9 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
             const int eb = (dir > 0 ? T_RQ : T_LQ);
 #pragma unroll
             for (int k = 0; k < NP; ++k) {
-              sc.vec(tvid(tail, eb + 0))[k * G] = q[k];
-              sc.vec(tvid(tail, eb + 1))[k * G] = p[k];
-              sc.vec(tvid(tail, eb + 2))[k * G] = g[k];
+              sc.st(tvid(tail, eb + 0), k, q[k]);
+              sc.st(tvid(tail, eb + 1), k, p[k]);
+              sc.st(tvid(tail, eb + 2), k, g[k]);
             }
             reg_edge = dir;
           } else {
@@ -541,7 +542,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
         }
         const double accept_stat = mean_tree_accept(tr);
 #pragma unroll
-        for (int k = 0; k < NP; ++k) q[k] = sc.vec(tvid(tail, T_PROPQ))[k * G];  // hmc_step.end.q
+        for (int k = 0; k < NP; ++k) q[k] = sc.ld(tvid(tail, T_PROPQ), k);  // hmc_step.end.q
 
         double* const ad = a.adapt + (size_t)chain * LMC_ADAPT_STRIDE;
         DualAvg da{__ldcg(ad + LMC_ADAPT_LOG_STEP), __ldcg(ad + LMC_ADAPT_LOG_BAR), __ldcg(ad + LMC_ADAPT_HBAR),
@@ -608,10 +609,16 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
     }
     if (sticky) {
       sticky_dead = dead;
+      if (completes_block(a, t)) {  // uniform across the warp
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) report_block(a, t);
+      }
       __syncwarp();
     } else {
       __threadfence();
       __syncwarp();
+      if (lane == 0 && completes_block(a, t)) report_block(a, t);
       if (lane == 0 && t + 1 < a.n_trans) {
         sv.prog[chain] = t + 1;
         __threadfence();

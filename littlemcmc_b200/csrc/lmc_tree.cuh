@@ -58,8 +58,47 @@ struct Scratch {
   double2* ws;  // global part (ids are absolute: the first n_smem slots are unused there)
   int n_smem;
   int lane;
-  __device__ __forceinline__ double2* vec(int id) const {
-    return (id < n_smem ? sm : ws) + (size_t)id * (G * NP) + lane;
+  // Pair k of vector `id` (this thread's word lane + k * G).  LMC_SCRATCH_MODE 0 (default): one generic LD / ST through
+  // a pointer selected at run time.  Modes 1 / 2 address the two homes in their own address spaces (LDS / STS for the
+  // shared-memory ids; plain or .cg global accesses for the workspace): measured SLOWER at every shape (1024 x 1000:
+  // 1.06e8 generic, 0.96e8 mode 1, 0.90e8 mode 2 leapfrog/s on the same box, profiles/r02g_scratch_modes.log) -- the
+  // second address computation per access costs registers the 128-register kernels do not have (spills), which outweighs
+  // the shorter LDS latency.  Kept for the record and for kernels with register headroom.
+#ifndef LMC_SCRATCH_MODE
+#define LMC_SCRATCH_MODE 0
+#endif
+  __device__ __forceinline__ double2 ld(int id, int k) const {
+#if LMC_SCRATCH_MODE == 0
+    return ((id < n_smem ? sm : ws) + (size_t)id * (G * NP) + lane)[k * G];
+#else
+    if (id < n_smem) {
+      const double2* p = sm + (size_t)id * (G * NP) + lane + k * G;
+      __builtin_assume(__isShared(p));
+      return *p;
+    }
+#if LMC_SCRATCH_MODE == 1
+    return ws[(size_t)id * (G * NP) + lane + k * G];
+#else
+    return __ldcg(ws + (size_t)id * (G * NP) + lane + k * G);
+#endif
+#endif
+  }
+  __device__ __forceinline__ void st(int id, int k, double2 v) const {
+#if LMC_SCRATCH_MODE == 0
+    ((id < n_smem ? sm : ws) + (size_t)id * (G * NP) + lane)[k * G] = v;
+#else
+    if (id < n_smem) {
+      double2* p = sm + (size_t)id * (G * NP) + lane + k * G;
+      __builtin_assume(__isShared(p));
+      *p = v;
+    } else {
+#if LMC_SCRATCH_MODE == 1
+      ws[(size_t)id * (G * NP) + lane + k * G] = v;
+#else
+      __stcg(ws + (size_t)id * (G * NP) + lane + k * G, v);
+#endif
+    }
+#endif
   }
 };
 
@@ -85,14 +124,14 @@ __device__ __forceinline__ void tree_init(const Scratch<G, NP>& sc, int tail, co
                                           const double2 (&p)[NP], const double2 (&g)[NP]) {
 #pragma unroll
   for (int k = 0; k < NP; ++k) {
-    sc.vec(tvid(tail, T_LQ))[k * G] = q[k];
-    sc.vec(tvid(tail, T_LP))[k * G] = p[k];
-    sc.vec(tvid(tail, T_LG))[k * G] = g[k];
-    sc.vec(tvid(tail, T_RQ))[k * G] = q[k];
-    sc.vec(tvid(tail, T_RP))[k * G] = p[k];
-    sc.vec(tvid(tail, T_RG))[k * G] = g[k];
-    sc.vec(tvid(tail, T_PSUM))[k * G] = p[k];
-    sc.vec(tvid(tail, T_PROPQ))[k * G] = q[k];
+    sc.st(tvid(tail, T_LQ), k, q[k]);
+    sc.st(tvid(tail, T_LP), k, p[k]);
+    sc.st(tvid(tail, T_LG), k, g[k]);
+    sc.st(tvid(tail, T_RQ), k, q[k]);
+    sc.st(tvid(tail, T_RP), k, p[k]);
+    sc.st(tvid(tail, T_RG), k, g[k]);
+    sc.st(tvid(tail, T_PSUM), k, p[k]);
+    sc.st(tvid(tail, T_PROPQ), k, q[k]);
   }
 }
 
@@ -123,13 +162,13 @@ __device__ __forceinline__ bool merge_level(const Scratch<G, NP>& sc, Group<G>& 
   double2 t1_lp[NP], t1_rp[NP], t1_ps[NP];
   if (lvl == 0) {
 #pragma unroll
-    for (int k = 0; k < NP; ++k) t1_lp[k] = t1_rp[k] = t1_ps[k] = sc.vec(vid_stack(0, 0))[k * G];
+    for (int k = 0; k < NP; ++k) t1_lp[k] = t1_rp[k] = t1_ps[k] = sc.ld(vid_stack(0, 0), k);
   } else {
 #pragma unroll
     for (int k = 0; k < NP; ++k) {
-      t1_lp[k] = sc.vec(vid_stack(lvl, 0))[k * G];
-      t1_rp[k] = sc.vec(vid_stack(lvl, 1))[k * G];
-      t1_ps[k] = sc.vec(vid_stack(lvl, 2))[k * G];
+      t1_lp[k] = sc.ld(vid_stack(lvl, 0), k);
+      t1_rp[k] = sc.ld(vid_stack(lvl, 1), k);
+      t1_ps[k] = sc.ld(vid_stack(lvl, 2), k);
     }
   }
   bool turn;
@@ -210,8 +249,8 @@ __device__ __forceinline__ void push_leaf(const Scratch<G, NP>& sc, StackScalars
   free_slots &= ~(1u << cur.pslot);
 #pragma unroll
   for (int k = 0; k < NP; ++k) {
-    sc.vec(vid_prop(cur.pslot))[k * G] = q[k];
-    sc.vec(vid_stack(0, 0))[k * G] = p[k];
+    sc.st(vid_prop(cur.pslot), k, q[k]);
+    sc.st(vid_stack(0, 0), k, p[k]);
   }
   if (sc.lane == 0) {
     ss->wm[0] = cur.w.m;
@@ -232,7 +271,7 @@ __device__ __forceinline__ bool merge_leaf_pair(const Scratch<G, NP>& sc, Group<
   double d2[2] = {0.0, 0.0};
 #pragma unroll
   for (int k = 0; k < NP; ++k) {
-    const double2 t1p = sc.vec(vid_stack(0, 0))[k * G];
+    const double2 t1p = sc.ld(vid_stack(0, 0), k);
     const double2 ps = add2(t1p, p[k]);            // p_sum = tree1.p_sum + tree2.p_sum (:390)
     d2[0] = dot2(d2[0], ps, mul2(var[k], t1p));    // p_sum . left.v
     d2[1] = dot2(d2[1], ps, mul2(var[k], p[k]));   // p_sum . right.v
@@ -265,17 +304,17 @@ __device__ __forceinline__ void push_cur(const Scratch<G, NP>& sc, StackScalars*
     cur.pslot = __ffs(free_slots) - 1;
     free_slots &= ~(1u << cur.pslot);
 #pragma unroll
-    for (int k = 0; k < NP; ++k) sc.vec(vid_prop(cur.pslot))[k * G] = q[k];
+    for (int k = 0; k < NP; ++k) sc.st(vid_prop(cur.pslot), k, q[k]);
   }
   if (lvl == 0) {
 #pragma unroll
-    for (int k = 0; k < NP; ++k) sc.vec(vid_stack(0, 0))[k * G] = p[k];
+    for (int k = 0; k < NP; ++k) sc.st(vid_stack(0, 0), k, p[k]);
   } else {
 #pragma unroll
     for (int k = 0; k < NP; ++k) {
-      sc.vec(vid_stack(lvl, 0))[k * G] = cur_lp[k];
-      sc.vec(vid_stack(lvl, 1))[k * G] = p[k];
-      sc.vec(vid_stack(lvl, 2))[k * G] = cur_ps[k];
+      sc.st(vid_stack(lvl, 0), k, cur_lp[k]);
+      sc.st(vid_stack(lvl, 1), k, p[k]);
+      sc.st(vid_stack(lvl, 2), k, cur_ps[k]);
     }
   }
   if (sc.lane == 0) {
@@ -301,10 +340,10 @@ __device__ __forceinline__ bool extend_top(const Scratch<G, NP>& sc, Group<G>& g
     tr.prop_logp = cur.plogp;
     if (cur.pslot == kLeafProp) {
 #pragma unroll
-      for (int k = 0; k < NP; ++k) sc.vec(tvid(tail, T_PROPQ))[k * G] = q[k];
+      for (int k = 0; k < NP; ++k) sc.st(tvid(tail, T_PROPQ), k, q[k]);
     } else {
 #pragma unroll
-      for (int k = 0; k < NP; ++k) sc.vec(tvid(tail, T_PROPQ))[k * G] = sc.vec(vid_prop(cur.pslot))[k * G];
+      for (int k = 0; k < NP; ++k) sc.st(tvid(tail, T_PROPQ), k, sc.ld(vid_prop(cur.pslot), k));
     }
   }
   tr.Wp = xf_add(tr.Wp, cur.w);    // log_size = logaddexp(log_size, tree.log_size)                     (:325)
@@ -312,9 +351,9 @@ __device__ __forceinline__ bool extend_top(const Scratch<G, NP>& sc, Group<G>& g
   double d6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
   for (int k = 0; k < NP; ++k) {
-    const double2 psum = add2(sc.vec(tvid(tail, T_PSUM))[k * G], cur_ps[k]);  // self.p_sum[:] += tree.p_sum (:329)
-    sc.vec(tvid(tail, T_PSUM))[k * G] = psum;
-    const double2 oLp = sc.vec(tvid(tail, T_LP))[k * G], oRp = sc.vec(tvid(tail, T_RP))[k * G];  // old edges' momenta
+    const double2 psum = add2(sc.ld(tvid(tail, T_PSUM), k), cur_ps[k]);  // self.p_sum[:] += tree.p_sum (:329)
+    sc.st(tvid(tail, T_PSUM), k, psum);
+    const double2 oLp = sc.ld(tvid(tail, T_LP), k), oRp = sc.ld(tvid(tail, T_RP), k);  // old edges' momenta
     const double2 voL = mul2(var[k], oLp), voR = mul2(var[k], oRp);
     const double2 vTl = mul2(var[k], cur_lp[k]), vTr = mul2(var[k], p[k]);
     if (dir > 0) {

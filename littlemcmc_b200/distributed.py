@@ -84,7 +84,7 @@ def _resolve_run(logp_dlogp_func, model_ndim, chains, random_seed, step, start, 
     rank = dist.get_rank(group)
     # keywords of the drivers (sample / distributed.sample); everything else configures the step method (init_nuts)
     driver_keys = ("init", "cores", "progressbar", "chain_idx", "callback", "mp_ctx", "pickle_backend", "device",
-                   "block", "return_device", "host_write", "stats_as", "_timing")
+                   "block", "return_device", "host_write", "stats_as", "single_launch", "_timing")
     nuts_kwargs = {k: kwargs.pop(k) for k in list(kwargs) if k not in driver_keys}
     # the seed list depends on the process-global NumPy stream when random_seed is None: resolve it once, broadcast
     box = [sampling._resolve_seeds(random_seed, chains) if rank == 0 else None]

@@ -226,11 +226,15 @@ def _alloc_outputs(chains, n_trans, trace, stats):
 
 
 def run_transitions(kind, chains, target, *, n_trans, iter0, n_tune, params, seeds=None, tapes=None,
-                    trace=None, stats=None, knobs=None, stream=None, events=None, step_size_override=None):
+                    trace=None, stats=None, knobs=None, stream=None, events=None, step_size_override=None,
+                    trace_skip=0, progress=None, progress_block=0):
     """Enqueue `n_trans` transitions of every chain (lmc_nuts_sample / lmc_hmc_sample).  Returns (trace, stats)
     device tensors [C, n_trans, D] and [C, n_trans, NSTATS].  Asynchronous on the current CUDA stream.
     `events`: optional pair of torch.cuda.Event recorded on the launching stream immediately around the library call
-    (bench.py times the launch with them, so host-side argument marshalling is not inside the bracket)."""
+    (bench.py times the launch with them, so host-side argument marshalling is not inside the bracket).
+    `trace_skip` / `progress` / `progress_block`: lmc_sampler_args of the same names (one launch for a whole run: the
+    first `trace_skip` transitions are not kept, `trace` holds the rest, and the int32 device counters `progress` tell the
+    caller which blocks of kept draws are final)."""
     lib = L.load()
     dev = chains.device
     Cn, D = chains.n_chains, chains.ndim
@@ -242,6 +246,11 @@ def run_transitions(kind, chains, target, *, n_trans, iter0, n_tune, params, see
         keep = _fill_base(a, kind, chains, n_trans=n_trans, iter0=iter0, n_tune=n_tune, params=params, seeds=seeds,
                           tapes=tapes, trace=trace, stats=stats, knobs=knobs, stream=stream,
                           step_size_override=step_size_override)
+        a.trace_skip, a.progress_block = int(trace_skip), int(progress_block)
+        if progress is not None:
+            assert progress.dtype == torch.int32 and progress.is_cuda
+            a.progress = progress.data_ptr()
+            keep.append(progress)
         user = isinstance(target, UserFusedTarget)
         if user:
             a.tune_group = 0                  # the kernel a user target is compiled into is the library's default choice

@@ -46,7 +46,7 @@ def _resolve_seeds(random_seed, chains):
 def sample(logp_dlogp_func, model_ndim, draws=1000, tune=1000, step=None, init="auto", chains=None, cores=None,
            start=None, progressbar=True, random_seed=None, discard_tuned_samples=True, chain_idx=0, callback=None,
            mp_ctx=None, pickle_backend="pickle", device=None, block=None, return_device=False, host_write="copy",
-           stats_as="dict", _timing=None, **kwargs):
+           stats_as="dict", single_launch=True, _timing=None, **kwargs):
     """Draw samples with the given step method; signature and return value of reference `sample` (sampling.py:35-222).
 
     Returns ``(trace, stats)``: ``trace`` float64 ``[chains, draws, model_ndim]``; ``stats`` a dict of arrays
@@ -65,7 +65,10 @@ def sample(logp_dlogp_func, model_ndim, draws=1000, tune=1000, step=None, init="
     copied out by the copy engine on a side stream while the next block samples (measured: 66 ms for 3.3 GB of draws
     next to 54 ms of sampling); ``"direct"``: the sampler kernel stores each draw straight into the mapped pinned
     buffer (no staging; measured slower, 74 ms, because the stores back-pressure the sampling groups; fused targets
-    only); ``stats_as="tensor"`` (with ``return_device``): the statistics as the ONE ``[chains, draws, 13]`` device
+    only); ``single_launch`` (default True): with a fused or user-source density and a host trace the whole run is ONE
+    kernel launch -- the kernel skips discarded tuning draws itself and reports finished blocks of kept draws through
+    device counters, which the copy engine follows (False: one launch per block of transitions, as for callbacks);
+    ``stats_as="tensor"`` (with ``return_device``): the statistics as the ONE ``[chains, draws, 13]`` device
     tensor the kernels write (columns = ``step._stat_columns``) instead of a dict of views of it.
     """
     import time as _time
@@ -128,6 +131,47 @@ def sample(logp_dlogp_func, model_ndim, draws=1000, tune=1000, step=None, init="
     stats_blocks = []
     done, blk = 0, 0
     interrupted = False
+    # ---- host trace, fused (or user-source) density, no per-draw hook: ONE launch for the whole run ----------------------
+    # The kernel keeps the kept draws in a device trace, skips the discarded tuning draws itself (trace_skip) and counts
+    # finished chains per block of kept draws (progress); the copy engine ships every block to the pinned host trace as
+    # soon as its counter is full, while the same launch keeps sampling.  No launch boundaries: no drains (the last
+    # transitions of a block otherwise run on a partly idle GPU, ~25 times per run at the headline size).
+    single = (not return_device and not direct and callback is None and n_keep > 0 and T > 0
+              and step._fused_target() is not None and step._step_rand is None
+              and not getattr(step.potential, "_dense", False) and single_launch
+              and chains * n_keep * D * 8 <= 0.5 * torch.cuda.mem_get_info(dev)[0]
+              and chains * T < (1 << 31))
+    if single:
+        pb = max(1, min(block, n_keep))
+        n_blocks = (n_keep + pb - 1) // pb
+        trace_dev = torch.empty(chains, n_keep, D, dtype=torch.float64, device=dev)
+        progress = torch.zeros(n_blocks, dtype=torch.int32, device=dev)
+        progress_host = torch.zeros(n_blocks, dtype=torch.int32).pin_memory()
+        _, st = step._run(T, int(tune), trace=trace_dev, trace_skip=keep_from, progress=progress, progress_block=pb)
+        stats_blocks.append(st)
+        _mark("enqueue")
+        lib = L.load()
+        shipped, idle = 0, 0
+        with torch.cuda.stream(copy_stream):
+            while shipped < n_blocks:
+                progress_host.copy_(progress, non_blocking=True)
+                copy_stream.synchronize()
+                counts = progress_host.numpy()
+                ready = shipped
+                while ready < n_blocks and int(counts[ready]) == chains:
+                    ready += 1
+                if ready == shipped:
+                    idle += 1
+                    if idle > 4:
+                        _time.sleep(5e-5)                  # nothing new: do not hammer the driver while the kernel works
+                    continue
+                idle = 0
+                lo, hi = shipped * pb, min(n_keep, ready * pb)   # consecutive finished blocks go out as one copy
+                src, dst = trace_dev[:, lo:hi], host_trace[:, lo:hi]
+                L.check(lib.lmc_memcpy2d_d2h(dst.data_ptr(), dst.stride(0) * 8, src.data_ptr(), src.stride(0) * 8,
+                                             (hi - lo) * D * 8, chains, copy_stream.cuda_stream), "lmc_memcpy2d_d2h")
+                shipped = ready
+        done = T
     try:
         while done < T:
             kept = done >= keep_from

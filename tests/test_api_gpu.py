@@ -303,3 +303,26 @@ def test_device_streams_are_the_documented_philox_function():
         for t in range(n_trans):
             assert np.array_equal(uniforms[c, t], philox.uniforms(seed, iter0 + t, u_stride)), (seed, t)
             np.testing.assert_allclose(normals[c, t], philox.normals(seed, iter0 + t, D), rtol=1e-13, atol=1e-14)
+
+
+@pytest.mark.parametrize("D,chains,method", [(37, 300, "nuts"), (1000, 96, "nuts"), (600, 40, "nuts"), (20, 64, "hmc")])
+@pytest.mark.parametrize("discard", [True, False])
+def test_single_launch_host_trace_equals_blockwise_launches(D, chains, method, discard):
+    """sample() with a host trace runs the whole run as ONE launch (the kernel skips discarded tuning draws and reports
+    finished blocks of kept draws through device counters the copy engine follows): bit-identical to one launch per
+    block, for the chunked warp kernel, the lean and register kernels and HMC, with a block that does not divide the run."""
+    import littlemcmc_b200 as lmc
+    sigma = 10 ** np.linspace(-0.5, 0.5, D)
+    tgt = lmc.targets.DiagGaussian(sigma=sigma)
+    out = []
+    for single in (True, False):
+        cls = lmc.NUTS if method == "nuts" else lmc.HamiltonianMC
+        step = cls(tgt, D, potential=lmc.QuadPotentialDiagAdapt(D, np.zeros(D), np.ones(D), 10))
+        out.append(lmc.sample(tgt, D, draws=23, tune=31, step=step, chains=chains, start=np.zeros(D), random_seed=5,
+                              discard_tuned_samples=discard, block=7, single_launch=single, progressbar=False))
+        assert step.iter_count == 54 and not step.tune
+    (t1, s1), (t2, s2) = out
+    assert t1.shape == (chains, 23 if discard else 54, D)
+    assert np.array_equal(t1, t2)
+    for k in s1:
+        assert np.array_equal(s1[k], s2[k]), k

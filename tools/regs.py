@@ -5,7 +5,7 @@ import sys
 
 src = sys.argv[1]
 cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
-       "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-c", src, "-o", "/tmp/regs_tmp.o"] + sys.argv[2:]
+       "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-I", "include", "-c", src, "-o", "/tmp/regs_tmp.o"] + sys.argv[2:]
 out = subprocess.run(cmd, capture_output=True, text=True)
 txt = out.stderr + out.stdout
 if out.returncode:
