@@ -59,6 +59,36 @@ __host__ __device__ inline SchedView sched_view(void* workspace, int n_chains) {
 }
 constexpr unsigned kDeadBit = 0x80000000u;
 
+// One thread of a group takes the next unit: chain (bit 31 = dead flag) or -1 when the launch is over, and the index of
+// the chain's next transition.  The ring slot is ZEROED once read: a pusher only ever writes into a consumed slot, so a
+// pusher that stalls between taking its ticket and storing the entry cannot be lapped by the ticket one ring later
+// (the late store used to overwrite the newer entry and the popper of that ticket spun forever).
+__device__ __forceinline__ void sched_pop(const SchedView& sv, unsigned total_units, unsigned n_chains, int& chain, int& t) {
+  chain = -1;
+  t = 0;
+  const unsigned h = atomicAdd(&sv.ctr[0], 1u);
+  if (h >= total_units) return;
+  volatile unsigned long long* e = sv.ring + (h % n_chains);
+  unsigned long long v = *e;
+  while ((unsigned)(v >> 32) != h + 1u) {  // only when the queue ran dry (fewer chains than groups, or the tail)
+    __nanosleep(100);
+    v = *e;
+  }
+  __threadfence();  // acquire: the previous owner's state writes are ordered before its push
+  *e = 0ull;        // consumed
+  chain = (int)(unsigned)v;
+  t = *(volatile int*)(sv.prog + (chain & 0x7fffffff));
+}
+// Hand the chain back for its transition t + 1 (the caller fenced its state writes).
+__device__ __forceinline__ void sched_push(const SchedView& sv, unsigned n_chains, int chain, int t_next, bool dead) {
+  sv.prog[chain] = t_next;
+  __threadfence();
+  const unsigned tk = atomicAdd(&sv.ctr[1], 1u);
+  const unsigned long long entry = ((unsigned long long)(tk + 1u) << 32) | (dead ? kDeadBit : 0u) | (unsigned)chain;
+  unsigned long long* slot = sv.ring + (tk % n_chains);
+  while (atomicCAS(slot, 0ull, entry) != 0ull) __nanosleep(100);  // wait for the slot's previous entry to be consumed
+}
+
 // lmc_sampler_args.progress: after transition t of a chain is globally visible (the caller fenced), one thread of the
 // group reports the kept-draw block it completes, if any
 __device__ __forceinline__ bool completes_block(const lmc_sampler_args& a, int t) {
@@ -144,18 +174,7 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
     // ---- pop the next (chain, transition) unit ---------------------------------------------------------------------
     int chain = -1, t = 0;
     if (lane == 0) {
-      const unsigned h = atomicAdd(&sv.ctr[0], 1u);
-      if (h < total_units) {
-        volatile unsigned long long* e = sv.ring + (h % (unsigned)a.n_chains);
-        unsigned long long v = *e;
-        while ((unsigned)(v >> 32) != h + 1u) {  // only when the queue ran dry (fewer chains than groups, or the tail)
-          __nanosleep(100);
-          v = *e;
-        }
-        __threadfence();  // acquire: the previous owner's state writes are ordered before its push
-        chain = (int)(unsigned)v;  // bit 31 = dead flag
-        t = *(volatile int*)(sv.prog + (chain & 0x7fffffff));
-      }
+      sched_pop(sv, total_units, (unsigned)a.n_chains, chain, t);
       if constexpr (G > 32) {
         s_pop[0] = chain;
         s_pop[1] = t;
@@ -432,13 +451,7 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
     __threadfence();  // release: this thread's state writes become visible before the push below
     group_barrier<G>();
     if (lane == 0 && completes_block(a, t)) report_block(a, t);
-    if (lane == 0 && t + 1 < a.n_trans) {
-      sv.prog[chain] = t + 1;
-      __threadfence();
-      const unsigned tk = atomicAdd(&sv.ctr[1], 1u);
-      *(volatile unsigned long long*)(sv.ring + (tk % (unsigned)a.n_chains)) =
-          ((unsigned long long)(tk + 1u) << 32) | (dead ? kDeadBit : 0u) | (unsigned)chain;
-    }
+    if (lane == 0 && t + 1 < a.n_trans) sched_push(sv, (unsigned)a.n_chains, chain, t + 1, dead);
   }
 }
 

@@ -73,18 +73,7 @@ __global__ void __launch_bounds__(G, MINCTAS) sampler_lean_kernel(const lmc_samp
     // ---- pop the next (chain, transition) unit (lmc_sampler.cuh: scheduler) -------------------------------------------
     int chain = -1, t = 0;
     if (lane == 0) {
-      const unsigned h = atomicAdd(&sv.ctr[0], 1u);
-      if (h < total_units) {
-        volatile unsigned long long* e = sv.ring + (h % (unsigned)a.n_chains);
-        unsigned long long v = *e;
-        while ((unsigned)(v >> 32) != h + 1u) {
-          __nanosleep(100);
-          v = *e;
-        }
-        __threadfence();
-        chain = (int)(unsigned)v;
-        t = *(volatile int*)(sv.prog + (chain & 0x7fffffff));
-      }
+      sched_pop(sv, total_units, (unsigned)a.n_chains, chain, t);
       s_pop[0] = chain;
       s_pop[1] = t;
     }
@@ -459,13 +448,7 @@ __global__ void __launch_bounds__(G, MINCTAS) sampler_lean_kernel(const lmc_samp
     __threadfence();
     __syncthreads();
     if (lane == 0 && completes_block(a, t)) report_block(a, t);
-    if (lane == 0 && t + 1 < a.n_trans) {
-      sv.prog[chain] = t + 1;
-      __threadfence();
-      const unsigned tk = atomicAdd(&sv.ctr[1], 1u);
-      *(volatile unsigned long long*)(sv.ring + (tk % (unsigned)a.n_chains)) =
-          ((unsigned long long)(tk + 1u) << 32) | (dead ? kDeadBit : 0u) | (unsigned)chain;
-    }
+    if (lane == 0 && t + 1 < a.n_trans) sched_push(sv, (unsigned)a.n_chains, chain, t + 1, dead);
   }
 }
 

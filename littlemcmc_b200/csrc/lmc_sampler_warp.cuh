@@ -133,20 +133,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
         t = t_next++;
       }
     } else {
-      if (lane == 0) {
-        const unsigned h = atomicAdd(&sv.ctr[0], 1u);
-        if (h < total_units) {
-          volatile unsigned long long* e = sv.ring + (h % (unsigned)a.n_chains);
-          unsigned long long v = *e;
-          while ((unsigned)(v >> 32) != h + 1u) {
-            __nanosleep(200);
-            v = *e;
-          }
-          __threadfence();
-          chain = (int)(unsigned)v;
-          t = *(volatile int*)(sv.prog + (chain & 0x7fffffff));
-        }
-      }
+      if (lane == 0) sched_pop(sv, total_units, (unsigned)a.n_chains, chain, t);
       chain = __shfl_sync(FULL, chain, 0);
       t = __shfl_sync(FULL, t, 0);
     }
@@ -619,17 +606,10 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
       __threadfence();
       __syncwarp();
       if (lane == 0 && completes_block(a, t)) report_block(a, t);
-      if (lane == 0 && t + 1 < a.n_trans) {
-        sv.prog[chain] = t + 1;
-        __threadfence();
-        const unsigned tk = atomicAdd(&sv.ctr[1], 1u);
-        *(volatile unsigned long long*)(sv.ring + (tk % (unsigned)a.n_chains)) =
-            ((unsigned long long)(tk + 1u) << 32) | (dead ? kDeadBit : 0u) | (unsigned)chain;
-      }
+      if (lane == 0 && t + 1 < a.n_trans) sched_push(sv, (unsigned)a.n_chains, chain, t + 1, dead);
     }
   }
 }
-
 
 #ifndef __CUDACC_RTC__
 // `kern`: a sampler_warp_kernel instantiation of this library or a cudaKernel_t compiled at run time for a user target

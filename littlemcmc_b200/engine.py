@@ -373,7 +373,7 @@ class CallbackRun:
         with torch.cuda.device(dev):
             self.begin()
             if cuda_graph in (True, "device"):
-                self._run_device_loop(iters_per_graph or 2)
+                self._run_device_loop(iters_per_graph or 4)
             elif cuda_graph == "replay":
                 self._run_graphed(iters_per_graph or 8)
             elif cuda_graph:

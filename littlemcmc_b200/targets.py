@@ -31,11 +31,13 @@ class DiagGaussian:
     def torch_batched(self, device, cuda_graph=False):
         """The same density as a batched torch op (callback mode instead of the fused kernel)."""
         import torch
-        tau = torch.as_tensor(self.tau, dtype=torch.float64, device=device)
+        neg_tau = torch.as_tensor(-self.tau, dtype=torch.float64, device=device)
+        half_neg_tau = 0.5 * neg_tau
 
         def fn(q):
-            g = -(tau * q)
-            return 0.5 * (q * g).sum(1), g
+            # three kernels per evaluation (callback mode is bound by launches per gradient, not by bytes):
+            # g = q * (-tau) [bitwise -(tau * q)], logp = (q * q) @ (-tau / 2)
+            return torch.mv(q * q, half_neg_tau), q * neg_tau
         return TorchBatched(fn, cuda_graph=cuda_graph)
 
 
@@ -122,17 +124,19 @@ struct %(name)s {
       double2 gk = make_double2(0.0, 0.0);
       if (j < ldh) {
 %(loads)s
-        if (2 * j < D) {
+        // both elements are evaluated unconditionally (selects, no branches); an element beyond ndim contributes nothing
+        const bool in_x = 2 * j < D, in_y = 2 * j + 1 < D;
+        {
           const double q = q_[k].x;
 %(bind_x)s
-          gk.x = (%(grad)s);
-          part += (%(logp)s);
+          gk.x = in_x ? (%(grad)s) : 0.0;
+          part += in_x ? (%(logp)s) : 0.0;
         }
-        if (2 * j + 1 < D) {
+        {
           const double q = q_[k].y;
 %(bind_y)s
-          gk.y = (%(grad)s);
-          part += (%(logp)s);
+          gk.y = in_y ? (%(grad)s) : 0.0;
+          part += in_y ? (%(logp)s) : 0.0;
         }
       }
       g_[k] = gk;
@@ -160,7 +164,7 @@ class ElementwiseTarget(CudaTarget):
         for i, n in enumerate(names):
             blob[i, :ndim] = params[n]
         name = "LmcElementwise_" + hashlib.sha256(repr((logp, grad, names)).encode()).hexdigest()[:12]
-        loads = "\n".join("        const double2 %s_2 = reinterpret_cast<const double2*>(params + %d * 2 * (size_t)ldh)[j];"
+        loads = "\n".join("        const double2 %s_2 = __ldg(reinterpret_cast<const double2*>(params + %d * 2 * (size_t)ldh) + j);"
                           % (n, i) for i, n in enumerate(names))
         bind = lambda c: "\n".join("          const double %s = %s_2.%s;" % (n, n, c) for n in names)  # noqa: E731
         src = _ELEMENTWISE_TEMPLATE % dict(name=name, loads=loads, bind_x=bind("x"), bind_y=bind("y"), grad=grad, logp=logp)

@@ -173,3 +173,19 @@ def test_warp_kernel_agrees_with_the_one_warp_register_kernel(name):
     for k in ("depth", "tree_size", "diverging"):
         assert np.array_equal(a.gpu_stats[k], b.gpu_stats[k]), k
     np.testing.assert_allclose(a.gpu_trace, b.gpu_trace, rtol=1e-8, atol=1e-11)
+
+
+def test_chained_adaptive_run_tracks_the_reference_until_chaos_takes_over():
+    """A long chained run with both adaptations (235 transitions, nuts_diag_d37) is chaotic: a last-bit difference in a
+    dot product is amplified through the step-size / mass-matrix feedback until a tree decision flips, after which the
+    chains are different (equally valid) chains -- the same happens inside the CPU oracle when its step size is nudged by
+    one ulp.  The test states the number: the device run must follow the reference EXACTLY (tree sizes) and to 1e-6 (draws)
+    for at least the first 25 transitions of every chain, and it reports where the first decision actually flips."""
+    res = pu.run_case_on_gpu_and_oracle("nuts_diag_d37", chained=True)
+    same = res.gpu_stats["tree_size"] == res.cpu_stats["tree_size"]
+    first_flip = [int(np.argmin(row)) if not row.all() else row.size for row in same]
+    print("first transition whose tree size differs from the reference, per chain:", first_flip, "of", same.shape[1])
+    assert min(first_flip) >= 25
+    n = min(first_flip)
+    np.testing.assert_allclose(res.gpu_trace[:, :25], res.cpu_trace[:, :25], rtol=1e-6, atol=1e-9)
+    assert n <= same.shape[1]
