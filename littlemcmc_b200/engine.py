@@ -14,6 +14,7 @@ from . import _lib as L
 
 _GRAPH_RES = {}   # device -> (side stream, CUDA-graph memory pool) of callback mode
 _GRAPH_KEEP = {}  # device -> most recent captured graph (keeps the shared pool in use)
+_GRAPH_BRANCH = {}  # device -> extra capture streams (parallel branches of a callback graph)
 
 # launches of this library's kernels enqueued by this process (bench.py reports the count inside its timed region)
 LAUNCH_COUNT = {"kernels": 0}
@@ -85,6 +86,19 @@ class DeviceChains:
         if self._workspace is None or self._workspace.numel() < nbytes:
             self._workspace = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
         return self._workspace
+
+    def rows(self, lo, hi):
+        """The chains [lo, hi) as a DeviceChains sharing this one's memory (own workspace)."""
+        key = (int(lo), int(hi))
+        views = self.__dict__.setdefault("_row_views", {})
+        if key not in views:
+            v = object.__new__(DeviceChains)
+            v.device, v.ndim, v.ld, v.n_chains = self.device, self.ndim, self.ld, key[1] - key[0]
+            for name in ("q", "var", "mean_fg", "rawvar_fg", "mean_bg", "rawvar_bg", "adapt", "status"):
+                setattr(v, name, getattr(self, name)[key[0]:key[1]])
+            v._workspace = None
+            views[key] = v
+        return views[key]
 
 
 class FusedTarget:
@@ -306,7 +320,7 @@ class CallbackRun:
     around a user gradient callback.  The loop body (callback + advance) can be captured in a CUDA graph."""
 
     def __init__(self, kind, chains, callback, *, n_trans, iter0, n_tune, params, seeds=None, tapes=None, trace=None,
-                 stats=None, stream=None, step_size_override=None):
+                 stats=None, stream=None, step_size_override=None, n_running=None):
         self.lib = L.load()
         self.kind, self.chains, self.callback = kind, chains, callback
         dev, Cn, D = chains.device, chains.n_chains, chains.ndim
@@ -314,7 +328,8 @@ class CallbackRun:
         self.q_eval = torch.zeros(Cn, chains.ld, dtype=torch.float64, device=dev)
         self.g_eval = torch.zeros(Cn, chains.ld, dtype=torch.float64, device=dev)
         self.logp_eval = torch.zeros(Cn, dtype=torch.float64, device=dev)
-        self.n_running = torch.zeros(1, dtype=torch.int32, device=dev)
+        # chains that still need gradient evaluations; several runs over disjoint chains may share one counter
+        self.n_running = torch.zeros(1, dtype=torch.int32, device=dev) if n_running is None else n_running
         self.n_running_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.c = L.CallbackArgs()
         with torch.cuda.device(dev):
@@ -397,56 +412,11 @@ class CallbackRun:
 
     def _capture_iterations(self, n_iters, keep_graph):
         """Capture `n_iters` x (callback + advance) on torch's capture stream.  -> torch.cuda.CUDAGraph"""
-        dev = self.chains.device
-        # one side stream and ONE graph memory pool per device, shared by every capture of this process: a fresh
-        # pool per graph means cudaMalloc at capture and a synchronising cudaFree when the graph dies, every call
-        key = str(dev)
-        if key not in _GRAPH_RES:
-            _GRAPH_RES[key] = (torch.cuda.Stream(device=dev), torch.cuda.graph_pool_handle())
-        side, pool = _GRAPH_RES[key]
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):       # warm the callback up outside capture (lazy init, autotune, allocations)
-            evaluate_callback(self.callback, self.q_eval[:, :self.chains.ndim])
-        torch.cuda.current_stream(dev).wait_stream(side)
-        graph = torch.cuda.CUDAGraph(keep_graph=True) if keep_graph else torch.cuda.CUDAGraph()
-        before = self.n_evals
-        # capture_begin / capture_end directly: the torch.cuda.graph context manager also runs gc.collect(),
-        # empty_cache() and a device synchronisation on entry (tens of milliseconds per run, measured)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            graph.capture_begin(pool=pool)
-            try:
-                for _ in range(n_iters):
-                    self.iteration()
-            finally:
-                graph.capture_end()
-        torch.cuda.current_stream(dev).wait_stream(side)
-        self.n_evals = before
-        # the shared pool must never lose its last user between two captures (the allocator retires a pool whose use
-        # count drops to zero and asserts if it is handed out again): keep the newest graph of this device alive
-        _GRAPH_KEEP[key] = graph
-        return graph
+        return _capture_runs([self], n_iters, keep_graph)
 
     def _run_device_loop(self, iters_per_body):
         """The whole run as one graph launch: WHILE(n_running > 0) { callback; advance; } on the device."""
-        dev = self.chains.device
-        graph = self._capture_iterations(iters_per_body, keep_graph=True)
-        iters = torch.zeros(1, dtype=torch.int32, device=dev)
-        loop = C.c_void_p()
-        max_bodies = (self.max_iters + iters_per_body - 1) // iters_per_body
-        L.check(self.lib.lmc_callback_loop_create(C.c_void_p(int(graph.raw_cuda_graph())), _ptr(self.n_running),
-                                                  _ptr(iters), max_bodies, C.byref(loop)), "lmc_callback_loop_create")
-        try:
-            stream = torch.cuda.current_stream(dev)
-            L.check(self.lib.lmc_callback_loop_launch(loop, C.c_void_p(stream.cuda_stream)), "lmc_callback_loop_launch")
-            left, done = int(self.n_running.item()), int(iters.item())       # the one synchronisation of the run
-        finally:
-            torch.cuda.synchronize(dev)
-            self.lib.lmc_callback_loop_destroy(loop)
-        self.n_evals += done * iters_per_body
-        LAUNCH_COUNT["kernels"] += done * (iters_per_body + 1)               # advance kernels + the loop-condition kernel
-        if left != 0:
-            raise L.LmcError("callback mode: chains still running after %d gradient evaluations" % (done * iters_per_body))
+        _device_loop([self], iters_per_body)
 
     def _run_graphed(self, iters_per_graph):
         graph = self._capture_iterations(iters_per_graph, keep_graph=False)
@@ -461,9 +431,115 @@ class CallbackRun:
         raise L.LmcError("callback mode: chains still running after %d gradient evaluations" % it)
 
 
+def _capture_runs(runs, n_iters, keep_graph):
+    """Capture `n_iters` x (callback + advance) of every run, the runs on PARALLEL branches of one graph (forked streams):
+    the kernels of callback mode are tiny, so independent batches of chains overlap on the GPU."""
+    dev = runs[0].chains.device
+    # one side stream (+ branch streams) and ONE graph memory pool per device, shared by every capture of this process:
+    # a fresh pool per graph means cudaMalloc at capture and a synchronising cudaFree when the graph dies, every call
+    key = str(dev)
+    if key not in _GRAPH_RES:
+        _GRAPH_RES[key] = (torch.cuda.Stream(device=dev), torch.cuda.graph_pool_handle())
+    side, pool = _GRAPH_RES[key]
+    branches = _GRAPH_BRANCH.setdefault(key, [])
+    while len(branches) < len(runs) - 1:
+        branches.append(torch.cuda.Stream(device=dev))
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):       # warm the callback up outside capture (lazy init, autotune, allocations)
+        for r in runs:
+            evaluate_callback(r.callback, r.q_eval[:, :r.chains.ndim])
+    torch.cuda.current_stream(dev).wait_stream(side)
+    graph = torch.cuda.CUDAGraph(keep_graph=True) if keep_graph else torch.cuda.CUDAGraph()
+    before = [r.n_evals for r in runs]
+    # capture_begin / capture_end directly: the torch.cuda.graph context manager also runs gc.collect(),
+    # empty_cache() and a device synchronisation on entry (tens of milliseconds per run, measured)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        graph.capture_begin(pool=pool)
+        try:
+            for k, r in enumerate(runs):
+                st = side if k == 0 else branches[k - 1]
+                if k:
+                    st.wait_stream(side)                     # fork
+                with torch.cuda.stream(st):
+                    for _ in range(n_iters):
+                        r.iteration()
+            for k in range(1, len(runs)):
+                side.wait_stream(branches[k - 1])            # join
+        finally:
+            graph.capture_end()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    for r, b in zip(runs, before):
+        r.n_evals = b
+    # the shared pool must never lose its last user between two captures (the allocator retires a pool whose use
+    # count drops to zero and asserts if it is handed out again): keep the newest graph of this device alive
+    _GRAPH_KEEP[key] = graph
+    return graph
+
+
+def _device_loop(runs, iters_per_body):
+    """All runs (disjoint chains, one shared n_running counter) as ONE graph launch: a WHILE conditional node whose body
+    is `iters_per_body` x (callback; advance) per run on parallel branches, looping on the device until every chain of
+    every run has finished (include/lmc_b200.h: lmc_callback_loop_*)."""
+    lib, dev = runs[0].lib, runs[0].chains.device
+    n_running = runs[0].n_running
+    assert all(r.n_running is n_running for r in runs)
+    graph = _capture_runs(runs, iters_per_body, keep_graph=True)
+    iters = torch.zeros(1, dtype=torch.int32, device=dev)
+    loop = C.c_void_p()
+    max_bodies = (max(r.max_iters for r in runs) + iters_per_body - 1) // iters_per_body
+    L.check(lib.lmc_callback_loop_create(C.c_void_p(int(graph.raw_cuda_graph())), _ptr(n_running), _ptr(iters), max_bodies,
+                                         C.byref(loop)), "lmc_callback_loop_create")
+    try:
+        stream = torch.cuda.current_stream(dev)
+        L.check(lib.lmc_callback_loop_launch(loop, C.c_void_p(stream.cuda_stream)), "lmc_callback_loop_launch")
+        left, done = int(n_running.item()), int(iters.item())       # the one synchronisation of the run
+    finally:
+        torch.cuda.synchronize(dev)
+        lib.lmc_callback_loop_destroy(loop)
+    for r in runs:
+        r.n_evals += done * iters_per_body
+    LAUNCH_COUNT["kernels"] += done * (iters_per_body * len(runs) + 1)   # advance kernels + the loop-condition kernel
+    if left != 0:
+        raise L.LmcError("callback mode: chains still running after %d gradient evaluations" % (done * iters_per_body))
+
+
 def run_transitions_callback(kind, chains, callback, *, n_trans, iter0, n_tune, params, seeds=None, tapes=None,
-                             trace=None, stats=None, cuda_graph=False, step_size_override=None):
-    """Callback-mode counterpart of run_transitions (synchronous: returns when every chain has finished)."""
+                             trace=None, stats=None, cuda_graph=False, step_size_override=None, split=None):
+    """Callback-mode counterpart of run_transitions (synchronous: returns when every chain has finished).
+    `split` (device-driven loop only, default 1): number of batches the chains are cut into, each with its own callback
+    evaluation and advance kernel on a parallel branch of the graph.  Measured SLOWER than one batch on B200 (1024 x 100:
+    4.4e7 -> 2.8e7 leapfrog/s with 2 batches; 8192 x 50: 2.2e7 -> 1.2e7 with 4): the nodes of a WHILE body execute one
+    after the other whatever the graph's shape, so the cost is per node, and splitting doubles the nodes.  Kept as an
+    option for callbacks whose kernels are large enough to fill the GPU only together."""
+    from .targets import TorchBatched
+    Cn = chains.n_chains
+    if cuda_graph in (True, "device") and isinstance(callback, TorchBatched) and n_trans > 0 and Cn > 0:
+        K = int(split) if split else 1
+        K = max(1, min(K, Cn))
+        if K > 1:
+            dev = chains.device
+            trace, stats = _alloc_outputs(chains, n_trans, trace, stats)
+            n_running = torch.zeros(1, dtype=torch.int32, device=dev)
+            bounds = np.linspace(0, Cn, K + 1).astype(int)
+            cut = lambda x, lo, hi: None if x is None else x[lo:hi]    # noqa: E731
+            if tapes is not None:
+                tapes = tuple(torch.as_tensor(t, dtype=torch.float64, device=dev) for t in tapes)
+            if step_size_override is not None:
+                step_size_override = torch.as_tensor(step_size_override, dtype=torch.float64, device=dev)
+            runs = []
+            for lo, hi in zip(bounds[:-1], bounds[1:]):
+                runs.append(CallbackRun(kind, chains.rows(lo, hi), callback, n_trans=n_trans, iter0=iter0, n_tune=n_tune,
+                                        params=params, seeds=cut(seeds, lo, hi),
+                                        tapes=None if tapes is None else (tapes[0][lo:hi], tapes[1][lo:hi]),
+                                        trace=trace[lo:hi], stats=stats[lo:hi],
+                                        step_size_override=cut(step_size_override, lo, hi), n_running=n_running))
+            with torch.cuda.device(dev):
+                for r in runs:
+                    r.begin()
+                n_running.fill_(Cn)          # every begin wrote its own batch size: the shared counter is their sum
+                _device_loop(runs, 4)
+            return trace, stats
     run = CallbackRun(kind, chains, callback, n_trans=n_trans, iter0=iter0, n_tune=n_tune, params=params, seeds=seeds,
                       tapes=tapes, trace=trace, stats=stats, step_size_override=step_size_override)
     run.run(cuda_graph=cuda_graph)

@@ -13,6 +13,27 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-9
 
 
+def test_device_loop_over_parallel_batches_of_chains():
+    """engine.run_transitions_callback(split=K): K batches of chains on parallel branches of the loop body, one shared
+    counter of running chains -- the same bits as one batch."""
+    import torch
+    from littlemcmc_b200 import _lib as L, engine
+    case, _ = gc.load("nuts_diag_d37")
+    D, Cn, T = int(case["ndim"]), 11, 12
+    cb = pu.torch_callback(case, cuda_graph=True)
+    params = pu.gpu_params(case)
+    seeds = engine.seeds_tensor(np.arange(Cn) * 7919 + 3, "cuda:0")
+    outs = []
+    for split in (1, 3):
+        ch = pu.gpu_chains(case, Cn)
+        tr, st = engine.run_transitions_callback(L.KIND_NUTS, ch, cb, n_trans=T, iter0=0, n_tune=8, params=params,
+                                                 seeds=seeds, cuda_graph=True, split=split)
+        torch.cuda.synchronize()
+        outs.append((tr.cpu().numpy(), st.cpu().numpy(), ch.adapt.cpu().numpy()))
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)
+
+
 def test_device_loop_transition_level_parity_deep_trees():
     """Depth-10 trees through the device-driven loop: ~1000 loop bodies per transition without the host."""
     res = pu.run_case_on_gpu_and_oracle("nuts_deep_d100", callback="torch-graph")
