@@ -61,6 +61,10 @@ __global__ void __launch_bounds__(G, MINCTAS) sampler_lean_kernel(const lmc_samp
   sc.n_smem = cfg.n_smem_vecs;
   sc.lane = lane;
   __shared__ int s_pop[2];
+  const auto var_f = [=](int k) { return s_var[k * G]; };
+  const auto cps_f = [=](int k) { return s_cps[k * G]; };
+  const auto set_cps = [=](int k, double2 v) { s_cps[k * G] = v; };
+  const auto no_lp = [](int, double2) {};  // the merged subtree's left edge stays where it is: referenced by id
   Group<G> grp(lane, red);
   const SchedView sv = sched_view(a.workspace, a.n_chains);
   const unsigned total_units = (unsigned)a.n_chains * (unsigned)a.n_trans;
@@ -202,85 +206,26 @@ __global__ void __launch_bounds__(G, MINCTAS) sampler_lean_kernel(const lmc_samp
               if (i + 1 < n_leaf_total) push_leaf<G, NP>(sc, ss, q, p, cur, free_slots);
               continue;  // (the single leaf of the first doubling stays in registers: cur_lp_id == -1)
             }
-            // ---- odd leaf: merge with stack entry 0 (nuts.py:387-417) ---------------------------------------------------
-            {
-              double d2[2] = {0.0, 0.0};
-#pragma unroll
-              for (int k = 0; k < NP; ++k) {
-                const double2 t1p = sc.ld(vid_stack(0, 0), k);
-                const double2 vk = s_var[k * G];
-                const double2 ps = add2(t1p, p[k]);
-                d2[0] = dot2(d2[0], ps, mul2(vk, t1p));
-                d2[1] = dot2(d2[1], ps, mul2(vk, p[k]));
-                s_cps[k * G] = ps;
-              }
-              grp.allreduce(d2);
-              const bool turn = (d2[0] <= 0) || (d2[1] <= 0);  // :391
-              cur_lp_id = vid_stack(0, 0);
-              const double u = next_uniform();
-              const XF nw = xf_add(XF{ss->wm[0], ss->we[0]}, cur.w);
-              const XF na = xf_add(XF{ss->am[0], ss->ae[0]}, cur.a);
-              const int t1_pslot = ss->pslot[0];
-              if (xf_u_less(u, nw, cur.w)) {
-                free_slots |= 1u << t1_pslot;
-              } else {
-                cur.pslot = t1_pslot;
-                cur.pE = ss->pE[0];
-                cur.plogp = ss->plogp[0];
-              }
-              cur.w = nw;
-              cur.a = na;
-              if (turn) {
-                fail = 2;
-                break;
-              }
+            // ---- odd leaf: merge with stack entry 0, then with level 1, 2, .. for every further trailing 1-bit of i
+            // (nuts.py:387-417; the arithmetic is lmc_tree.cuh's, the operands are reached where this kernel keeps them:
+            // var and the running p_sum in shared memory, the left edge by the id of the stack vector that holds it)
+            if (merge_leaves<G, NP>(sc, grp, ss, var_f, PairArray<NP>{p}, PairArray<NP>{p}, set_cps, no_lp, cur, free_slots,
+                                    next_uniform)) {
+              fail = 2;
+              break;
             }
+            cur_lp_id = vid_stack(0, 0);
             unsigned jbits = i >> 1;
             int lvl = 1;
             while (jbits & 1u) {  // merge with stack entry lvl >= 1
-              double d6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-              for (int k = 0; k < NP; ++k) {
-                const double2 t1_lp = sc.ld(vid_stack(lvl, 0), k);
-                const double2 t1_rp = sc.ld(vid_stack(lvl, 1), k);
-                const double2 t1_ps = sc.ld(vid_stack(lvl, 2), k);
-                const double2 c_lp = sc.ld(cur_lp_id, k);
-                const double2 c_ps = s_cps[k * G];
-                const double2 vk = s_var[k * G];
-                const double2 ps = add2(t1_ps, c_ps);   // :390
-                const double2 ps1 = add2(t1_ps, c_lp);  // :394
-                const double2 ps2 = add2(t1_rp, c_ps);  // :396
-                const double2 v1l = mul2(vk, t1_lp), v1r = mul2(vk, t1_rp);
-                const double2 v2l = mul2(vk, c_lp), v2r = mul2(vk, p[k]);
-                d6[0] = dot2(d6[0], ps, v1l);
-                d6[1] = dot2(d6[1], ps, v2r);
-                d6[2] = dot2(d6[2], ps1, v1l);
-                d6[3] = dot2(d6[3], ps1, v2l);
-                d6[4] = dot2(d6[4], ps2, v1r);
-                d6[5] = dot2(d6[5], ps2, v2r);
-                s_cps[k * G] = ps;
-              }
-              grp.allreduce(d6);
-              const bool turn = (d6[0] <= 0) || (d6[1] <= 0) || (d6[2] <= 0) || (d6[3] <= 0) || (d6[4] <= 0) || (d6[5] <= 0);
-              cur_lp_id = vid_stack(lvl, 0);
-              const double u = next_uniform();
-              const XF nw = xf_add(XF{ss->wm[lvl], ss->we[lvl]}, cur.w);
-              const XF na = xf_add(XF{ss->am[lvl], ss->ae[lvl]}, cur.a);
-              const int t1_pslot = ss->pslot[lvl];
-              if (xf_u_less(u, nw, cur.w)) {
-                free_slots |= 1u << t1_pslot;
-              } else {
-                if (cur.pslot != kLeafProp) free_slots |= 1u << cur.pslot;
-                cur.pslot = t1_pslot;
-                cur.pE = ss->pE[lvl];
-                cur.plogp = ss->plogp[lvl];
-              }
-              cur.w = nw;
-              cur.a = na;
-              if (turn) {
+              const int lp_id = cur_lp_id;
+              if (merge_upper<G, NP>(sc, grp, ss, lvl, var_f, PairArray<NP>{p},
+                                     [&](int k) { return sc.ld(lp_id, k); }, cps_f, set_cps, no_lp, cur, free_slots,
+                                     next_uniform)) {
                 fail = 2;
                 break;
               }
+              cur_lp_id = vid_stack(lvl, 0);
               jbits >>= 1;
               ++lvl;
             }
@@ -317,54 +262,12 @@ __global__ void __launch_bounds__(G, MINCTAS) sampler_lean_kernel(const lmc_samp
           }
           // ---- top of _Tree.extend (nuts.py:321-340): T.left.p = vec(cur_lp_id) or p, T.p_sum = s_cps or p --------------
           {
-            const double u = next_uniform();
-            if (xf_u_less(u, xf_add(tr.Wp, xf_one()), cur.w)) {
-              tr.prop_E = cur.pE;
-              tr.prop_logp = cur.plogp;
-              if (cur.pslot == kLeafProp) {
-#pragma unroll
-                for (int k = 0; k < NP; ++k) sc.st(tvid(tail, T_PROPQ), k, q[k]);
-              } else {
-#pragma unroll
-                for (int k = 0; k < NP; ++k) sc.st(tvid(tail, T_PROPQ), k, sc.ld(vid_prop(cur.pslot), k));
-              }
-            }
-            tr.Wp = xf_add(tr.Wp, cur.w);
-            tr.Acc = xf_add(tr.Acc, cur.a);
             const bool single = cur_lp_id < 0;
-            double d6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-            for (int k = 0; k < NP; ++k) {
-              const double2 c_ps = single ? p[k] : s_cps[k * G];
-              const double2 c_lp = single ? p[k] : sc.ld(cur_lp_id, k);
-              const double2 vk = s_var[k * G];
-              const double2 psum = add2(sc.ld(tvid(tail, T_PSUM), k), c_ps);  // :329
-              sc.st(tvid(tail, T_PSUM), k, psum);
-              const double2 oLp = sc.ld(tvid(tail, T_LP), k), oRp = sc.ld(tvid(tail, T_RP), k);
-              const double2 voL = mul2(vk, oLp), voR = mul2(vk, oRp);
-              const double2 vTl = mul2(vk, c_lp), vTr = mul2(vk, p[k]);
-              if (dir > 0) {
-                const double2 ps1 = add2(psum, c_lp);
-                const double2 ps2 = add2(oRp, c_ps);
-                d6[0] = dot2(d6[0], psum, voL);
-                d6[1] = dot2(d6[1], psum, vTr);
-                d6[2] = dot2(d6[2], ps1, voL);
-                d6[3] = dot2(d6[3], ps1, vTl);
-                d6[4] = dot2(d6[4], ps2, voR);
-                d6[5] = dot2(d6[5], ps2, vTr);
-              } else {
-                const double2 ps1 = add2(c_ps, oLp);
-                const double2 ps2 = add2(c_lp, psum);
-                d6[0] = dot2(d6[0], psum, vTr);
-                d6[1] = dot2(d6[1], psum, voR);
-                d6[2] = dot2(d6[2], ps1, vTr);
-                d6[3] = dot2(d6[3], ps1, voL);
-                d6[4] = dot2(d6[4], ps2, vTl);
-                d6[5] = dot2(d6[5], ps2, voR);
-              }
-            }
-            grp.allreduce(d6);
-            if ((d6[0] <= 0) || (d6[1] <= 0) || (d6[2] <= 0) || (d6[3] <= 0) || (d6[4] <= 0) || (d6[5] <= 0)) break;
+            const int lp_id = cur_lp_id;
+            if (extend_top_f<G, NP>(sc, grp, tail, dir, var_f, PairArray<NP>{q}, PairArray<NP>{p},
+                                    [&](int k) { return single ? p[k] : sc.ld(lp_id, k); },
+                                    [&](int k) { return single ? p[k] : s_cps[k * G]; }, cur, tr, next_uniform()))
+              break;
           }
           if (d + 1 < max_depth) {
             const int base = (dir > 0 ? T_RQ : T_LQ);

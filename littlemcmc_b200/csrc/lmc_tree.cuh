@@ -153,58 +153,23 @@ __device__ __forceinline__ bool leaf_init(double E, double logp, double E0, doub
   return true;
 }
 
-// One merge of _build_subtree (nuts.py:387-417): tree1 = stack entry `lvl`, tree2 = cur (right edge momentum p).
-// `u` is the uniform of logbern (:404), drawn by the caller even when the merged tree turns.  Returns `turning`.
-template <int G, int NP>
-__device__ __forceinline__ bool merge_level(const Scratch<G, NP>& sc, Group<G>& grp, const StackScalars* ss, int lvl,
-                                            const double2 (&var)[NP], const double2 (&p)[NP], double2 (&cur_lp)[NP],
-                                            double2 (&cur_ps)[NP], CurTree& cur, unsigned& free_slots, double u) {
-  double2 t1_lp[NP], t1_rp[NP], t1_ps[NP];
-  if (lvl == 0) {
-#pragma unroll
-    for (int k = 0; k < NP; ++k) t1_lp[k] = t1_rp[k] = t1_ps[k] = sc.ld(vid_stack(0, 0), k);
-  } else {
-#pragma unroll
-    for (int k = 0; k < NP; ++k) {
-      t1_lp[k] = sc.ld(vid_stack(lvl, 0), k);
-      t1_rp[k] = sc.ld(vid_stack(lvl, 1), k);
-      t1_ps[k] = sc.ld(vid_stack(lvl, 2), k);
-    }
-  }
-  bool turn;
-  if (lvl == 0) {
-    double d2[2] = {0.0, 0.0};
-#pragma unroll
-    for (int k = 0; k < NP; ++k) {
-      const double2 ps = add2(t1_ps[k], cur_ps[k]);     // p_sum = tree1.p_sum + tree2.p_sum (:390)
-      d2[0] = dot2(d2[0], ps, mul2(var[k], t1_lp[k]));  // p_sum . left.v
-      d2[1] = dot2(d2[1], ps, mul2(var[k], p[k]));      // p_sum . right.v
-      cur_ps[k] = ps;
-    }
-    grp.allreduce(d2);
-    turn = (d2[0] <= 0) || (d2[1] <= 0);  // :391
-  } else {
-    double d6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-    for (int k = 0; k < NP; ++k) {
-      const double2 ps = add2(t1_ps[k], cur_ps[k]);   // :390
-      const double2 ps1 = add2(t1_ps[k], cur_lp[k]);  // tree1.p_sum + tree2.left.p (:394)
-      const double2 ps2 = add2(t1_rp[k], cur_ps[k]);  // tree1.right.p + tree2.p_sum (:396)
-      const double2 v1l = mul2(var[k], t1_lp[k]), v1r = mul2(var[k], t1_rp[k]);
-      const double2 v2l = mul2(var[k], cur_lp[k]), v2r = mul2(var[k], p[k]);
-      d6[0] = dot2(d6[0], ps, v1l);
-      d6[1] = dot2(d6[1], ps, v2r);
-      d6[2] = dot2(d6[2], ps1, v1l);
-      d6[3] = dot2(d6[3], ps1, v2l);
-      d6[4] = dot2(d6[4], ps2, v1r);
-      d6[5] = dot2(d6[5], ps2, v2r);
-      cur_ps[k] = ps;
-    }
-    grp.allreduce(d6);
-    turn = (d6[0] <= 0) || (d6[1] <= 0) || (d6[2] <= 0) || (d6[3] <= 0) || (d6[4] <= 0) || (d6[5] <= 0);  // :391-398
-  }
-#pragma unroll
-  for (int k = 0; k < NP; ++k) cur_lp[k] = t1_lp[k];  // left edge of the merged tree
+// The vector operands of the tree arithmetic are reached through small accessor functors, so that ONE copy of every
+// formula (and of the reference's p_sum aliasing quirk) serves kernels that keep them in registers (arrays), in shared
+// memory (the lean kernel) or behind an id into the scratch (a left edge that is never copied): a functor `f(k)` returns
+// pair k of this thread; `set_ps(k, v)` / `set_lp(k, v)` store the merged subtree's p_sum / left-edge momentum.
+template <int NP>
+struct PairArray {
+  const double2 (&a)[NP];
+  __device__ __forceinline__ double2 operator()(int k) const { return a[k]; }
+};
+template <int NP>
+struct PairArrayOut {
+  double2 (&a)[NP];
+  __device__ __forceinline__ void operator()(int k, double2 v) const { a[k] = v; }
+};
+
+// scalar half of one merge (nuts.py:400-407): sizes, weighted accept sums, proposal choice with the uniform `u`
+__device__ __forceinline__ void merge_scalars(const StackScalars* ss, int lvl, CurTree& cur, unsigned& free_slots, double u) {
   const XF nw = xf_add(XF{ss->wm[lvl], ss->we[lvl]}, cur.w);  // log_size = logaddexp(...)             (:400)
   const XF na = xf_add(XF{ss->am[lvl], ss->ae[lvl]}, cur.a);  // log_weighted_accept_sum           (:401-403)
   // logbern(tree2.log_size - log_size) <=> u * size < size2                                            (:404)
@@ -219,7 +184,76 @@ __device__ __forceinline__ bool merge_level(const Scratch<G, NP>& sc, Group<G>& 
   }
   cur.w = nw;
   cur.a = na;
+}
+
+// One merge of _build_subtree at stack level lvl >= 1 (nuts.py:387-417): tree1 = stack entry `lvl`, tree2 = cur (left
+// edge momentum lp(k), p_sum ps(k), right edge momentum p(k)).  `u` is the uniform of logbern (:404), drawn by the
+// caller even when the merged tree turns.  Returns `turning`.
+template <int G, int NP, class VarF, class PF, class LpF, class PsF, class SetPsF, class SetLpF, class UF>
+__device__ __forceinline__ bool merge_upper(const Scratch<G, NP>& sc, Group<G>& grp, const StackScalars* ss, int lvl,
+                                            VarF var, PF p, LpF lp, PsF ps, SetPsF set_ps, SetLpF set_lp, CurTree& cur,
+                                            unsigned& free_slots, UF next_u) {
+  double d6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    const double2 t1_lp = sc.ld(vid_stack(lvl, 0), k), t1_rp = sc.ld(vid_stack(lvl, 1), k);
+    const double2 t1_ps = sc.ld(vid_stack(lvl, 2), k);
+    const double2 c_lp = lp(k), c_ps = ps(k), vk = var(k), pk = p(k);
+    const double2 nps = add2(t1_ps, c_ps);   // p_sum = tree1.p_sum + tree2.p_sum (:390)
+    const double2 ps1 = add2(t1_ps, c_lp);   // tree1.p_sum + tree2.left.p (:394)
+    const double2 ps2 = add2(t1_rp, c_ps);   // tree1.right.p + tree2.p_sum (:396)
+    const double2 v1l = mul2(vk, t1_lp), v1r = mul2(vk, t1_rp);
+    const double2 v2l = mul2(vk, c_lp), v2r = mul2(vk, pk);
+    d6[0] = dot2(d6[0], nps, v1l);
+    d6[1] = dot2(d6[1], nps, v2r);
+    d6[2] = dot2(d6[2], ps1, v1l);
+    d6[3] = dot2(d6[3], ps1, v2l);
+    d6[4] = dot2(d6[4], ps2, v1r);
+    d6[5] = dot2(d6[5], ps2, v2r);
+    set_ps(k, nps);
+    set_lp(k, t1_lp);  // left edge of the merged tree
+  }
+  grp.allreduce(d6);
+  const bool turn = (d6[0] <= 0) || (d6[1] <= 0) || (d6[2] <= 0) || (d6[3] <= 0) || (d6[4] <= 0) || (d6[5] <= 0);  // :391-398
+  merge_scalars(ss, lvl, cur, free_slots, next_u());  // the uniform is drawn whether or not the merged tree turns
   return turn;
+}
+
+// The same at level 0: tree1 is a single leaf (left.p == right.p == p_sum == the stored momentum), and so is tree2 when
+// it comes straight from the leapfrog (lp == ps == p).
+template <int G, int NP, class VarF, class PF, class PsF, class SetPsF, class SetLpF, class UF>
+__device__ __forceinline__ bool merge_leaves(const Scratch<G, NP>& sc, Group<G>& grp, const StackScalars* ss, VarF var,
+                                             PF p, PsF ps, SetPsF set_ps, SetLpF set_lp, CurTree& cur,
+                                             unsigned& free_slots, UF next_u) {
+  double d2[2] = {0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    const double2 t1p = sc.ld(vid_stack(0, 0), k);
+    const double2 vk = var(k);
+    const double2 nps = add2(t1p, ps(k));           // p_sum = tree1.p_sum + tree2.p_sum (:390)
+    d2[0] = dot2(d2[0], nps, mul2(vk, t1p));        // p_sum . left.v
+    d2[1] = dot2(d2[1], nps, mul2(vk, p(k)));       // p_sum . right.v
+    set_ps(k, nps);
+    set_lp(k, t1p);
+  }
+  grp.allreduce(d2);
+  const bool turn = (d2[0] <= 0) || (d2[1] <= 0);  // :391
+  merge_scalars(ss, 0, cur, free_slots, next_u());
+  return turn;
+}
+
+// One merge of _build_subtree (nuts.py:387-417) with every operand in registers: tree1 = stack entry `lvl`, tree2 = cur
+// (right edge momentum p).  Returns `turning`.
+template <int G, int NP>
+__device__ __forceinline__ bool merge_level(const Scratch<G, NP>& sc, Group<G>& grp, const StackScalars* ss, int lvl,
+                                            const double2 (&var)[NP], const double2 (&p)[NP], double2 (&cur_lp)[NP],
+                                            double2 (&cur_ps)[NP], CurTree& cur, unsigned& free_slots, double u) {
+  if (lvl == 0)
+    return merge_leaves<G, NP>(sc, grp, ss, PairArray<NP>{var}, PairArray<NP>{p}, PairArray<NP>{cur_ps},
+                               PairArrayOut<NP>{cur_ps}, PairArrayOut<NP>{cur_lp}, cur, free_slots, [u] { return u; });
+  return merge_upper<G, NP>(sc, grp, ss, lvl, PairArray<NP>{var}, PairArray<NP>{p}, PairArray<NP>{cur_lp},
+                            PairArray<NP>{cur_ps}, PairArrayOut<NP>{cur_ps}, PairArrayOut<NP>{cur_lp}, cur, free_slots,
+                            [u] { return u; });
 }
 
 // ---- level-0 specialisations used by the fused kernel ------------------------------------------------------------------
@@ -268,31 +302,8 @@ template <int G, int NP>
 __device__ __forceinline__ bool merge_leaf_pair(const Scratch<G, NP>& sc, Group<G>& grp, const StackScalars* ss,
                                                 const double2 (&var)[NP], const double2 (&p)[NP], double2 (&cur_lp)[NP],
                                                 double2 (&cur_ps)[NP], CurTree& cur, unsigned& free_slots, double u) {
-  double d2[2] = {0.0, 0.0};
-#pragma unroll
-  for (int k = 0; k < NP; ++k) {
-    const double2 t1p = sc.ld(vid_stack(0, 0), k);
-    const double2 ps = add2(t1p, p[k]);            // p_sum = tree1.p_sum + tree2.p_sum (:390)
-    d2[0] = dot2(d2[0], ps, mul2(var[k], t1p));    // p_sum . left.v
-    d2[1] = dot2(d2[1], ps, mul2(var[k], p[k]));   // p_sum . right.v
-    cur_ps[k] = ps;
-    cur_lp[k] = t1p;
-  }
-  grp.allreduce(d2);
-  const bool turn = (d2[0] <= 0) || (d2[1] <= 0);  // :391
-  const XF nw = xf_add(XF{ss->wm[0], ss->we[0]}, cur.w);  // :400
-  const XF na = xf_add(XF{ss->am[0], ss->ae[0]}, cur.a);  // :401-403
-  const int t1_pslot = ss->pslot[0];
-  if (xf_u_less(u, nw, cur.w)) {  // keep tree2's proposal (the current leaf, still in registers)       (:404-407)
-    free_slots |= 1u << t1_pslot;
-  } else {
-    cur.pslot = t1_pslot;
-    cur.pE = ss->pE[0];
-    cur.plogp = ss->plogp[0];
-  }
-  cur.w = nw;
-  cur.a = na;
-  return turn;
+  return merge_leaves<G, NP>(sc, grp, ss, PairArray<NP>{var}, PairArray<NP>{p}, PairArray<NP>{p}, PairArrayOut<NP>{cur_ps},
+                             PairArrayOut<NP>{cur_lp}, cur, free_slots, [u] { return u; });
 }
 
 // Push "cur" (right edge state q, p) as stack entry `lvl`.  One writer for the scalars (lane 0).
@@ -328,19 +339,17 @@ __device__ __forceinline__ void push_cur(const Scratch<G, NP>& sc, StackScalars*
   }
 }
 
-// Top of _Tree.extend after a completed subtree T = cur (nuts.py:321-340): T.left.p = cur_lp, T.right = z = (q, p),
-// T.p_sum = cur_ps.  `u` is the uniform of the biased progressive accept (:321-323).  Returns `turning`.
-template <int G, int NP>
-__device__ __forceinline__ bool extend_top(const Scratch<G, NP>& sc, Group<G>& grp, int tail, int dir,
-                                           const double2 (&var)[NP], const double2 (&q)[NP], const double2 (&p)[NP],
-                                           const double2 (&cur_lp)[NP], const double2 (&cur_ps)[NP],
-                                           const CurTree& cur, TrajScalars& tr, double u) {
+// Top of _Tree.extend after a completed subtree T = cur (nuts.py:321-340): T.left.p = lp(k), T.right = z = (q, p),
+// T.p_sum = ps(k).  `u` is the uniform of the biased progressive accept (:321-323).  Returns `turning`.
+template <int G, int NP, class VarF, class QF, class PF, class LpF, class PsF>
+__device__ __forceinline__ bool extend_top_f(const Scratch<G, NP>& sc, Group<G>& grp, int tail, int dir, VarF var, QF q,
+                                             PF p, LpF lp, PsF ps, const CurTree& cur, TrajScalars& tr, double u) {
   if (xf_u_less(u, xf_add(tr.Wp, xf_one()), cur.w)) {  // logbern(tree.log_size - self.log_size) :321-323
     tr.prop_E = cur.pE;
     tr.prop_logp = cur.plogp;
     if (cur.pslot == kLeafProp) {
 #pragma unroll
-      for (int k = 0; k < NP; ++k) sc.st(tvid(tail, T_PROPQ), k, q[k]);
+      for (int k = 0; k < NP; ++k) sc.st(tvid(tail, T_PROPQ), k, q(k));
     } else {
 #pragma unroll
       for (int k = 0; k < NP; ++k) sc.st(tvid(tail, T_PROPQ), k, sc.ld(vid_prop(cur.pslot), k));
@@ -351,16 +360,17 @@ __device__ __forceinline__ bool extend_top(const Scratch<G, NP>& sc, Group<G>& g
   double d6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
   for (int k = 0; k < NP; ++k) {
-    const double2 psum = add2(sc.ld(tvid(tail, T_PSUM), k), cur_ps[k]);  // self.p_sum[:] += tree.p_sum (:329)
+    const double2 c_ps = ps(k), c_lp = lp(k), vk = var(k), pk = p(k);
+    const double2 psum = add2(sc.ld(tvid(tail, T_PSUM), k), c_ps);  // self.p_sum[:] += tree.p_sum (:329)
     sc.st(tvid(tail, T_PSUM), k, psum);
     const double2 oLp = sc.ld(tvid(tail, T_LP), k), oRp = sc.ld(tvid(tail, T_RP), k);  // old edges' momenta
-    const double2 voL = mul2(var[k], oLp), voR = mul2(var[k], oRp);
-    const double2 vTl = mul2(var[k], cur_lp[k]), vTr = mul2(var[k], p[k]);
+    const double2 voL = mul2(vk, oLp), voR = mul2(vk, oRp);
+    const double2 vTl = mul2(vk, c_lp), vTr = mul2(vk, pk);
     if (dir > 0) {
       // left = old left, right = T.right; leftmost = old trajectory with the ALIASED (already updated) p_sum,
       // rightmost = T                                                          (:300-303, :333-339)
-      const double2 ps1 = add2(psum, cur_lp[k]);  // leftmost_p_sum + rightmost_begin.p
-      const double2 ps2 = add2(oRp, cur_ps[k]);   // leftmost_end.p + rightmost_p_sum
+      const double2 ps1 = add2(psum, c_lp);  // leftmost_p_sum + rightmost_begin.p
+      const double2 ps2 = add2(oRp, c_ps);   // leftmost_end.p + rightmost_p_sum
       d6[0] = dot2(d6[0], psum, voL);
       d6[1] = dot2(d6[1], psum, vTr);
       d6[2] = dot2(d6[2], ps1, voL);
@@ -370,8 +380,8 @@ __device__ __forceinline__ bool extend_top(const Scratch<G, NP>& sc, Group<G>& g
     } else {
       // left = T.right, right = old right; leftmost = T (begin = T.right, end = T.left), rightmost = old trajectory
       // with the aliased p_sum                                                 (:309-312, :333-339)
-      const double2 ps1 = add2(cur_ps[k], oLp);   // leftmost_p_sum + rightmost_begin.p
-      const double2 ps2 = add2(cur_lp[k], psum);  // leftmost_end.p + rightmost_p_sum
+      const double2 ps1 = add2(c_ps, oLp);   // leftmost_p_sum + rightmost_begin.p
+      const double2 ps2 = add2(c_lp, psum);  // leftmost_end.p + rightmost_p_sum
       d6[0] = dot2(d6[0], psum, vTr);
       d6[1] = dot2(d6[1], psum, voR);
       d6[2] = dot2(d6[2], ps1, vTr);
@@ -382,6 +392,14 @@ __device__ __forceinline__ bool extend_top(const Scratch<G, NP>& sc, Group<G>& g
   }
   grp.allreduce(d6);
   return (d6[0] <= 0) || (d6[1] <= 0) || (d6[2] <= 0) || (d6[3] <= 0) || (d6[4] <= 0) || (d6[5] <= 0);  // :333-340
+}
+template <int G, int NP>
+__device__ __forceinline__ bool extend_top(const Scratch<G, NP>& sc, Group<G>& grp, int tail, int dir,
+                                           const double2 (&var)[NP], const double2 (&q)[NP], const double2 (&p)[NP],
+                                           const double2 (&cur_lp)[NP], const double2 (&cur_ps)[NP],
+                                           const CurTree& cur, TrajScalars& tr, double u) {
+  return extend_top_f<G, NP>(sc, grp, tail, dir, PairArray<NP>{var}, PairArray<NP>{q}, PairArray<NP>{p},
+                             PairArray<NP>{cur_lp}, PairArray<NP>{cur_ps}, cur, tr, u);
 }
 
 // _Tree.stats: mean_tree_accept (nuts.py:419-425).  log_size > 0 <=> exp(log_size) - 1 > 0 in double;
