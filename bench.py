@@ -316,7 +316,8 @@ def measure_kernel(name, logp, steps, warmup, rank, dev, knobs=None, chains=0, t
     step._check_status()
     dev_ms = float(sum(step_ms))
     st = stats_all
-    leapfrogs = float(st[..., L.STAT_TREE_SIZE].sum().item())
+    leap_each = [float(x) for x in st[..., L.STAT_TREE_SIZE].sum((1, 2)).tolist()]
+    leapfrogs = float(sum(leap_each))
     peak, peak_src = hbm_peak()
     achieved = leapfrogs * 48 * D / (dev_ms * 1e-3) / 1e9      # 48*D algorithmic bytes per leapfrog
     out = dict(value=leapfrogs / (dev_ms * 1e-3), ms_per_step=dev_ms / steps, leapfrogs=leapfrogs, dev_ms=dev_ms,
@@ -326,6 +327,8 @@ def measure_kernel(name, logp, steps, warmup, rank, dev, knobs=None, chains=0, t
                mean_tree_accept=float(st[..., L.STAT_ACCEPT].mean().item()),
                divergences=float(st[..., L.STAT_DIVERGING].sum().item()),
                ms_per_step_median=float(np.median(step_ms)), ms_per_step_max=float(max(step_ms)),
+               ms_per_step_each=[round(float(x), 3) for x in step_ms], leapfrogs_per_step_each=leap_each,
+               max_tree_depth=float(st[..., L.STAT_DEPTH].max().item()),
                wall_ms_incl_flush=t_wall * 1e3, remeasured_after_host_stall=remeasured)
     del flush, stats_all
     return out, step, trace, seeds
@@ -491,12 +494,19 @@ def run_gpu_arm(args):
                  ("cfg5_shard", "cfg5", "fused"), ("cfg2_torch_graph", "cfg2", "torch-graph"),
                  ("cfg4_torch_graph", "cfg4", "torch-graph"), ("cfg2_user_source", "cfg2", "user-source")]
         for key, wl, mode in extra:
-            n_steps = 4 if mode == "torch-graph" else 8
+            # cfg4's run is 400 transitions (tune 300 + draws 100): 3 warm-up + 7 timed steps of 40 cover it exactly
+            n_steps = 4 if mode == "torch-graph" else 7 if wl == "cfg4" else 8
             try:
                 r, *_ = measure_kernel(wl, mode, n_steps, 3, rank, dev)
                 for k in ("leapfrogs", "dev_ms"):
                     r.pop(k)
                 r["workload"] = "%s: %s" % (wl, WORKLOADS[wl][6])
+                if wl == "cfg4":
+                    r["note"] = ("a launch lasts as long as its slowest chain: once the early depth cap (8, while tuning and "
+                                 "iter_count < 200) lifts, the few chains sitting in the funnel's neck with a tiny adapted "
+                                 "step size build depth-12 trees (4095 leapfrogs) transition after transition, strictly "
+                                 "one after the other, while the other chains' groups idle -- see ms_per_step_each: the steps "
+                                 "before iteration 200 run at the kernel's throughput, the later ones at one chain's latency")
                 configs[key] = r
             except Exception as e:            # a failed side measurement must not take the headline line down
                 configs[key] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
