@@ -42,6 +42,7 @@ struct WarpLayout {
   static constexpr int kRows = 6 * B - 6;            // table rows: 2B energy partials + (4B - 6) merge dot products
   static constexpr int kLog = (B == 2 ? 1 : B == 4 ? 2 : B == 8 ? 3 : 4);
   static_assert(B == 2 || B == 4 || B == 8 || B == 16, "chunk of 2, 4, 8 or 16 leaves");
+  static_assert(4 * B - 6 >= 8 && 4 * B - 6 + 2 >= 8, "TableGroup reuses 8 dot-product rows and 8 totals");
   // byte offsets inside a slot
   static constexpr int oRingP = 0;
   static constexpr int oPs = oRingP + B * VS * 16;
@@ -55,6 +56,42 @@ struct WarpLayout {
   static constexpr int nInts = B + 3 * (kLog + 1) + 1;
   static constexpr int oSS = ((oInts + nInts * 4) + 15) & ~15;
   static constexpr int kFixedBytes = ((oSS + (int)sizeof(StackScalars)) + 15) & ~15;  // scratch vectors follow
+};
+
+// The warp's all-reduce through the shared-memory table instead of a shuffle butterfly: lane n stores value n of every
+// lane into row n, lane r sums row r, everybody reads the N totals back.  Same latency as the butterfly (two warp
+// barriers and ~50 instructions instead of 5 x N shuffle pairs), but 4x less CODE per call site -- what matters here:
+// the kernel's warm footprint was 42 KB against a 32 KB instruction cache, 14 KB of it unrolled butterflies
+// (profiles/r02z_cfg2_ncu_full.md: no_instructions 26% of the stall samples).
+template <int LD>
+struct TableGroup {
+  int lane;
+  double* rows;  // [8][LD] partials (LD >= 34: conflict-free 128-bit row reads)
+  double* tot;   // [8] totals
+  template <int N>
+  __device__ __forceinline__ void allreduce(double (&v)[N]) {
+    static_assert(N <= 8, "TableGroup reduces up to 8 values");
+#pragma unroll
+    for (int n = 0; n < N; ++n) rows[n * LD + lane] = v[n];
+    __syncwarp();
+    if (lane < N) {
+      const double2* r = reinterpret_cast<const double2*>(rows + lane * LD);
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+      for (int k = 0; k < 16; k += 2) {
+        const double2 x = r[k], y = r[k + 1];
+        s0 += x.x;
+        s1 += x.y;
+        s2 += y.x;
+        s3 += y.y;
+      }
+      tot[lane] = (s0 + s1) + (s2 + s3);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int n = 0; n < N; ++n) v[n] = tot[n];
+    __syncwarp();  // the totals are read before the next reduction overwrites them
+  }
 };
 
 template <class Target, int NP, int B, int WPB, int MINB, bool TAPE>
@@ -89,7 +126,12 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
           (size_t)slot * cfg.ws_vecs * VS;
   sc.n_smem = cfg.n_smem_vecs;
   sc.lane = lane;
-  Group<G> grp(lane, nullptr);
+  // every all-reduce of this kernel goes through the table (TableGroup), on rows that are idle at that point:
+  //   grp   the two-value reductions inside a leapfrog (a target's pre-sums, the initial energy): the dot-product rows,
+  //         which phase 1 does not touch;   tgrp  the six-value reductions of the stack merges and of extend (once per
+  //         chunk / doubling, after the chunk's table has been consumed): its first rows.  Totals land in vDot.
+  TableGroup<LY::kRowLd> grp{lane, part + 2 * B * LY::kRowLd, vDot};
+  TableGroup<LY::kRowLd> tgrp{lane, part, vDot};
   const SchedView sv = sched_view(a.workspace, a.n_chains);
   const unsigned total_units = (unsigned)a.n_chains * (unsigned)a.n_trans;
 
@@ -448,8 +490,9 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
               }
               int lvl = bc;
               for (unsigned cb = c; cb & 1u; cb >>= 1, ++lvl) {
-                __builtin_assume(lvl >= 1);
-                if (merge_level<G, NP>(sc, grp, ss, lvl, var, p, cur_lp, cur_ps, cur, free_slots, next_uniform())) {
+                if (merge_upper<G, NP>(sc, tgrp, ss, lvl, PairArray<NP>{var}, PairArray<NP>{p}, PairArray<NP>{cur_lp},
+                                       PairArray<NP>{cur_ps}, PairArrayOut<NP>{cur_ps}, PairArrayOut<NP>{cur_lp}, cur,
+                                       free_slots, next_uniform)) {
                   fail = 2;
                   break;
                 }
@@ -512,7 +555,9 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
 #pragma unroll
               for (int k = 0; k < NP; ++k) qprop[k] = ring_q[(size_t)(pidx * NP + k) * 32];
             }
-            if (extend_top<G, NP>(sc, grp, tail, dir, var, qprop, p, cur_lp, cur_ps, cur, tr, next_uniform())) break;  // :340
+            if (extend_top_f<G, NP>(sc, tgrp, tail, dir, PairArray<NP>{var}, PairArray<NP>{qprop}, PairArray<NP>{p},
+                                    PairArray<NP>{cur_lp}, PairArray<NP>{cur_ps}, cur, tr, next_uniform()))
+              break;  // :340
           }
           if (d + 1 < max_depth) {
             const int eb = (dir > 0 ? T_RQ : T_LQ);

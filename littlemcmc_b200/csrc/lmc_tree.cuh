@@ -189,8 +189,8 @@ __device__ __forceinline__ void merge_scalars(const StackScalars* ss, int lvl, C
 // One merge of _build_subtree at stack level lvl >= 1 (nuts.py:387-417): tree1 = stack entry `lvl`, tree2 = cur (left
 // edge momentum lp(k), p_sum ps(k), right edge momentum p(k)).  `u` is the uniform of logbern (:404), drawn by the
 // caller even when the merged tree turns.  Returns `turning`.
-template <int G, int NP, class VarF, class PF, class LpF, class PsF, class SetPsF, class SetLpF, class UF>
-__device__ __forceinline__ bool merge_upper(const Scratch<G, NP>& sc, Group<G>& grp, const StackScalars* ss, int lvl,
+template <int G, int NP, class Grp, class VarF, class PF, class LpF, class PsF, class SetPsF, class SetLpF, class UF>
+__device__ __forceinline__ bool merge_upper(const Scratch<G, NP>& sc, Grp& grp, const StackScalars* ss, int lvl,
                                             VarF var, PF p, LpF lp, PsF ps, SetPsF set_ps, SetLpF set_lp, CurTree& cur,
                                             unsigned& free_slots, UF next_u) {
   double d6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
@@ -221,8 +221,8 @@ __device__ __forceinline__ bool merge_upper(const Scratch<G, NP>& sc, Group<G>& 
 
 // The same at level 0: tree1 is a single leaf (left.p == right.p == p_sum == the stored momentum), and so is tree2 when
 // it comes straight from the leapfrog (lp == ps == p).
-template <int G, int NP, class VarF, class PF, class PsF, class SetPsF, class SetLpF, class UF>
-__device__ __forceinline__ bool merge_leaves(const Scratch<G, NP>& sc, Group<G>& grp, const StackScalars* ss, VarF var,
+template <int G, int NP, class Grp, class VarF, class PF, class PsF, class SetPsF, class SetLpF, class UF>
+__device__ __forceinline__ bool merge_leaves(const Scratch<G, NP>& sc, Grp& grp, const StackScalars* ss, VarF var,
                                              PF p, PsF ps, SetPsF set_ps, SetLpF set_lp, CurTree& cur,
                                              unsigned& free_slots, UF next_u) {
   double d2[2] = {0.0, 0.0};
@@ -341,8 +341,8 @@ __device__ __forceinline__ void push_cur(const Scratch<G, NP>& sc, StackScalars*
 
 // Top of _Tree.extend after a completed subtree T = cur (nuts.py:321-340): T.left.p = lp(k), T.right = z = (q, p),
 // T.p_sum = ps(k).  `u` is the uniform of the biased progressive accept (:321-323).  Returns `turning`.
-template <int G, int NP, class VarF, class QF, class PF, class LpF, class PsF>
-__device__ __forceinline__ bool extend_top_f(const Scratch<G, NP>& sc, Group<G>& grp, int tail, int dir, VarF var, QF q,
+template <int G, int NP, class Grp, class VarF, class QF, class PF, class LpF, class PsF>
+__device__ __forceinline__ bool extend_top_f(const Scratch<G, NP>& sc, Grp& grp, int tail, int dir, VarF var, QF q,
                                              PF p, LpF lp, PsF ps, const CurTree& cur, TrajScalars& tr, double u) {
   if (xf_u_less(u, xf_add(tr.Wp, xf_one()), cur.w)) {  // logbern(tree.log_size - self.log_size) :321-323
     tr.prop_E = cur.pE;
