@@ -168,6 +168,20 @@ LMC_COLD double2 philox_normal_pair(uint64_t seed, int64_t it, uint32_t j) {
   return make_double2(rad * c, rad * s);
 }
 
+// 1/sqrt(x) of NP pairs, IEEE sqrt and divide as in inv_sqrt_cold: ONE out-of-line copy of the code, a rolled loop with
+// the two chains of a pair interleaved (code size matters more than the last bit of instruction-level parallelism here)
+template <int NP>
+static __device__ __noinline__ void inv_sqrt_pairs(const double2 (&v)[NP], double2 (&out)[NP]) {
+#pragma unroll 1
+  for (int k = 0; k < NP; ++k) out[k] = make_double2(1.0 / sqrt(v[k].x), 1.0 / sqrt(v[k].y));
+}
+// r / w for NP pairs (IEEE divide), same shape
+template <int NP>
+static __device__ __noinline__ void div_pairs(const double2 (&r)[NP], double w, double2 (&out)[NP]) {
+#pragma unroll 1
+  for (int k = 0; k < NP; ++k) out[k] = make_double2(r[k].x / w, r[k].y / w);
+}
+
 // ---- thread group owning one chain ---------------------------------------------------------------------------
 template <int G>
 struct Group {

@@ -57,6 +57,14 @@ bool pick_lean_shape(int ndim, int group, int* G, int* NP);
 // with tune_group == 1
 int run_gauss_nuts_warp(const lmc_sampler_args& a, const DiagGaussian& t);
 int run_funnel_nuts_warp(const lmc_sampler_args& a, const Funnel& t);
+// chunked CTA-per-chain NUTS kernel (lmc_sampler_cta.cuh): 128 threads per chain, up to 1024 dimensions; forced with
+// tune_group == 2 (203 / 204: with 3 / 4 resident CTAs per SM)
+int run_gauss_nuts_cta(const lmc_sampler_args& a, const DiagGaussian& t);
+int run_funnel_nuts_cta(const lmc_sampler_args& a, const Funnel& t);
+constexpr int kCtaRingMax = 4;  // largest position ring (leaves per chunk) of that kernel
+static bool use_cta_kernel(int kind, int ndim, int tune_group) {
+  return kind == KIND_NUTS && (ndim + 1) / 2 <= 512 && (tune_group == 2 || tune_group == 203 || tune_group == 204);
+}
 static bool use_warp_kernel(int kind, int ndim, int tune_group) {
   return kind == KIND_NUTS && (ndim + 1) / 2 <= 128 && (tune_group == 0 || tune_group == 1);
 }
@@ -73,11 +81,13 @@ static int sample_entry(const lmc_sampler_args* a, int kind) {
   if (a->n_chains == 0 || a->n_trans == 0) return LMC_OK;
   if (a->target.kind == LMC_TARGET_DIAG_GAUSSIAN) {
     DiagGaussian t{reinterpret_cast<const double2*>(a->target.tau)};
+    if (use_cta_kernel(kind, a->ndim, a->tune_group)) return run_gauss_nuts_cta(*a, t);
     if (use_warp_kernel(kind, a->ndim, a->tune_group)) return run_gauss_nuts_warp(*a, t);
     if (lean_group(a, kind)) return run_gauss_nuts_lean(*a, t, lean_group(a, kind));
     return kind == KIND_NUTS ? run_gauss_nuts(*a, t) : run_gauss_hmc(*a, t);
   }
   Funnel t{1.0 / (a->target.v_scale * a->target.v_scale), 0.5 * (double)(a->ndim - 1)};
+  if (use_cta_kernel(kind, a->ndim, a->tune_group)) return run_funnel_nuts_cta(*a, t);
   if (use_warp_kernel(kind, a->ndim, a->tune_group)) return run_funnel_nuts_warp(*a, t);
   if (lean_group(a, kind)) return run_funnel_nuts_lean(*a, t, lean_group(a, kind));
   return kind == KIND_NUTS ? run_funnel_nuts(*a, t) : run_funnel_hmc(*a, t);
@@ -91,6 +101,17 @@ extern "C" int64_t lmc_workspace_bytes(int32_t kind, int32_t n_chains, int32_t n
   if (kind == lmc::KIND_HMC) return (int64_t)lmc::sched_bytes(n_chains);
   if (kind != lmc::KIND_NUTS || max_treedepth < 1 || max_treedepth > lmc::kMaxDepth) return LMC_ERR_UNSUPPORTED;
   lmc::Shape s;
+  if (lmc::use_cta_kernel(kind, ndim, tune_group)) {
+    // one CTA of 128 threads per slot, at most 16 per SM; scratch = tree stack + trajectory + the position ring
+    int dev = 0, n_sm = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    (void)cudaGetLastError();
+    const int np = (ndim + 1) / 2 <= 256 ? 2 : 4;
+    long long slots = (long long)n_sm * 16;
+    if (slots > n_chains) slots = n_chains < 1 ? 1 : n_chains;
+    return (long long)lmc::sched_bytes(n_chains) + slots * (lmc::ws_vecs_nuts(max_treedepth) + lmc::kCtaRingMax) *
+                                                       (long long)(128 * np) * (long long)sizeof(double2);
+  }
   if (lmc::use_warp_kernel(kind, ndim, tune_group)) {
     // one warp per slot, at most 32 one-warp CTAs per SM; scratch = tree stack + trajectory + the largest position ring
     int dev = 0, n_sm = 148;

@@ -41,50 +41,69 @@ __host__ __device__ constexpr int block_threads() { return G >= 64 ? G : 128; }
 // leapfrogs), and the number of chains is rarely a multiple of the resident groups: with a static chain -> group
 // assignment the launch lasts as long as its unluckiest group, with the FIFO every group stays busy until the
 // queue drains.  Results do not depend on the schedule: all randomness is a function of (chain seed, iteration).
-//   header: unsigned head, tail, pad[2];  unsigned long long ring[n_chains] = (ticket + 1) << 32 | dead << 31 | chain;
-//           int prog[n_chains] = index of the chain's next transition within this call
-// A chain is in the ring at most once, so a ring of n_chains entries never overwrites an unread entry.
+//   header: unsigned head, tail, pad[2];  unsigned long long ring[n_chains] = (ticket + 1) << 32 | dead << 31 | unit,
+//           unit = chain * n_trans + index of the chain's next transition within this call (< 2^31, checked at launch)
+// A chain is in the ring at most once, so a ring of n_chains entries never overwrites an unread entry.  The entry says
+// everything about the unit, so a pop is two dependent L2 round trips (ticket, entry) and a push two (ticket, publish).
 struct SchedView {
   unsigned* ctr;             // [0] = head (pop tickets), [1] = tail (push tickets)
   unsigned long long* ring;  // [n_chains]
-  int* prog;                 // [n_chains]
+  unsigned n_trans;
 };
 __host__ __device__ inline size_t sched_bytes(int n_chains) {
   return (((size_t)16 + (size_t)n_chains * 12) + 255) & ~(size_t)255;
 }
-__host__ __device__ inline SchedView sched_view(void* workspace, int n_chains) {
+__host__ __device__ inline SchedView sched_view(void* workspace, int n_chains, int n_trans) {
   unsigned* c = reinterpret_cast<unsigned*>(workspace);
-  unsigned long long* r = reinterpret_cast<unsigned long long*>(c + 4);
-  return SchedView{c, r, reinterpret_cast<int*>(r + n_chains)};
+  return SchedView{c, reinterpret_cast<unsigned long long*>(c + 4), (unsigned)n_trans};
 }
 constexpr unsigned kDeadBit = 0x80000000u;
 
-// One thread of a group takes the next unit: chain (bit 31 = dead flag) or -1 when the launch is over, and the index of
-// the chain's next transition.  The ring slot is ZEROED once read: a pusher only ever writes into a consumed slot, so a
-// pusher that stalls between taking its ticket and storing the entry cannot be lapped by the ticket one ring later
-// (the late store used to overwrite the newer entry and the popper of that ticket spun forever).
-__device__ __forceinline__ void sched_pop(const SchedView& sv, unsigned total_units, unsigned n_chains, int& chain, int& t) {
+__device__ __forceinline__ void sched_decode(const SchedView& sv, unsigned long long v, int& chain, int& t) {
+  const unsigned unit = (unsigned)v & 0x7fffffffu;
+  const unsigned c = unit / sv.n_trans;
+  t = (int)(unit - c * sv.n_trans);
+  chain = (int)(c | ((unsigned)v & kDeadBit));
+}
+// A pop in three pieces, so that a kernel can issue the memory operations early and consume them late (the chunked CTA
+// kernel takes the ticket of its NEXT unit when a transition starts and reads the entry while the epilogue runs):
+//   ticket  position in the pop order;  peek  one look at the ticket's ring entry (0 when the launch has no such unit);
+//   take    wait until the entry is there, consume it.  Taking a ticket early cannot deadlock: a group only ever WAITS in
+//   take, after it has pushed its own chain, and every ticket below total_units is filled by some push.
+__device__ __forceinline__ unsigned sched_ticket(const SchedView& sv) { return atomicAdd(&sv.ctr[0], 1u); }
+__device__ __forceinline__ unsigned long long sched_peek(const SchedView& sv, unsigned ticket, unsigned total_units,
+                                                         unsigned n_chains) {
+  if (ticket >= total_units) return 0ull;
+  return *(volatile unsigned long long*)(sv.ring + (ticket % n_chains));
+}
+// The ring slot is ZEROED once read: a pusher only ever writes into a consumed slot, so a pusher that stalls between
+// taking its ticket and storing the entry cannot be lapped by the ticket one ring later (the late store used
+// to overwrite the newer entry and the popper of that ticket spun forever).
+__device__ __forceinline__ void sched_take(const SchedView& sv, unsigned ticket, unsigned long long v, unsigned total_units,
+                                           unsigned n_chains, int& chain, int& t) {
   chain = -1;
   t = 0;
-  const unsigned h = atomicAdd(&sv.ctr[0], 1u);
-  if (h >= total_units) return;
-  volatile unsigned long long* e = sv.ring + (h % n_chains);
-  unsigned long long v = *e;
-  while ((unsigned)(v >> 32) != h + 1u) {  // only when the queue ran dry (fewer chains than groups, or the tail)
+  if (ticket >= total_units) return;
+  volatile unsigned long long* e = sv.ring + (ticket % n_chains);
+  while ((unsigned)(v >> 32) != ticket + 1u) {  // only when the queue ran dry (fewer chains than groups, or the tail)
     __nanosleep(100);
     v = *e;
   }
   __threadfence();  // acquire: the previous owner's state writes are ordered before its push
   *e = 0ull;        // consumed
-  chain = (int)(unsigned)v;
-  t = *(volatile int*)(sv.prog + (chain & 0x7fffffff));
+  sched_decode(sv, v, chain, t);
 }
-// Hand the chain back for its transition t + 1 (the caller fenced its state writes).
+// One thread of a group takes the next unit: chain (bit 31 = dead flag) or -1 when the launch is over, and the index of
+// the chain's next transition.
+__device__ __forceinline__ void sched_pop(const SchedView& sv, unsigned total_units, unsigned n_chains, int& chain, int& t) {
+  const unsigned h = sched_ticket(sv);
+  sched_take(sv, h, sched_peek(sv, h, total_units, n_chains), total_units, n_chains, chain, t);
+}
+// Hand the chain back for its transition t_next (the caller fenced its state writes).
 __device__ __forceinline__ void sched_push(const SchedView& sv, unsigned n_chains, int chain, int t_next, bool dead) {
-  sv.prog[chain] = t_next;
-  __threadfence();
   const unsigned tk = atomicAdd(&sv.ctr[1], 1u);
-  const unsigned long long entry = ((unsigned long long)(tk + 1u) << 32) | (dead ? kDeadBit : 0u) | (unsigned)chain;
+  const unsigned long long entry = ((unsigned long long)(tk + 1u) << 32) | (dead ? kDeadBit : 0u) |
+                                   ((unsigned)chain * sv.n_trans + (unsigned)t_next);
   unsigned long long* slot = sv.ring + (tk % n_chains);
   while (atomicCAS(slot, 0ull, entry) != 0ull) __nanosleep(100);  // wait for the slot's previous entry to be consumed
 }
@@ -100,17 +119,14 @@ __device__ __forceinline__ void report_block(const lmc_sampler_args& a, int t) {
   atomicAdd(a.progress + (t - a.trace_skip) / a.progress_block, 1);
 }
 
-static __global__ void sched_init_kernel(void* workspace, int n_chains) {
-  const SchedView sv = sched_view(workspace, n_chains);
+static __global__ void sched_init_kernel(void* workspace, int n_chains, int n_trans) {
+  const SchedView sv = sched_view(workspace, n_chains, n_trans);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) {
     sv.ctr[0] = 0u;
     sv.ctr[1] = (unsigned)n_chains;
   }
-  if (i < n_chains) {
-    sv.ring[i] = ((unsigned long long)(i + 1) << 32) | (unsigned)i;
-    sv.prog[i] = 0;
-  }
+  if (i < n_chains) sv.ring[i] = ((unsigned long long)(i + 1) << 32) | ((unsigned)i * (unsigned)n_trans);
 }
 
 
@@ -163,7 +179,7 @@ __global__ void __launch_bounds__(block_threads<G>(), min_ctas<G, NP>()) sampler
   sc.lane = lane;
   __shared__ int s_pop[2];
   Group<G> grp(lane, red);
-  const SchedView sv = sched_view(a.workspace, a.n_chains);
+  const SchedView sv = sched_view(a.workspace, a.n_chains, a.n_trans);
   const unsigned total_units = (unsigned)a.n_chains * (unsigned)a.n_trans;
 
   const int D = a.ndim;
@@ -524,7 +540,7 @@ int launch_kernel(const void* kern, const lmc_sampler_args& a, const void* tgt) 
   const long long need = (long long)sched_bytes(a.n_chains) + grid * CPB * (long long)cfg.ws_vecs * (long long)vec_bytes;
   if (need > a.workspace_bytes) return LMC_ERR_WORKSPACE;
   if ((long long)a.n_chains * a.n_trans >= (1ll << 31)) return LMC_ERR_UNSUPPORTED;  // 32-bit scheduler tickets
-  sched_init_kernel<<<(a.n_chains + 255) / 256, 256, 0, (cudaStream_t)a.stream>>>(a.workspace, a.n_chains);
+  sched_init_kernel<<<(a.n_chains + 255) / 256, 256, 0, (cudaStream_t)a.stream>>>(a.workspace, a.n_chains, a.n_trans);
   void* kargs[] = {const_cast<lmc_sampler_args*>(&a), const_cast<void*>(tgt), &cfg};
   LMC_CUDA(cudaLaunchKernel(kern, dim3((unsigned)grid), dim3(BLOCK), kargs, smem, (cudaStream_t)a.stream));
   LMC_CUDA(cudaGetLastError());

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(G, MINCTAS) sampler_lean_kernel(const lmc_samp
   const auto set_cps = [=](int k, double2 v) { s_cps[k * G] = v; };
   const auto no_lp = [](int, double2) {};  // the merged subtree's left edge stays where it is: referenced by id
   Group<G> grp(lane, red);
-  const SchedView sv = sched_view(a.workspace, a.n_chains);
+  const SchedView sv = sched_view(a.workspace, a.n_chains, a.n_trans);
   const unsigned total_units = (unsigned)a.n_chains * (unsigned)a.n_trans;
 
   const int D = a.ndim;
@@ -393,7 +393,7 @@ int launch_lean(const lmc_sampler_args& a, const Target& tgt) {
   const long long need = (long long)sched_bytes(a.n_chains) + grid * (long long)cfg.ws_vecs * (long long)vec_bytes;
   if (need > a.workspace_bytes) return LMC_ERR_WORKSPACE;
   if ((long long)a.n_chains * a.n_trans >= (1ll << 31)) return LMC_ERR_UNSUPPORTED;
-  sched_init_kernel<<<(a.n_chains + 255) / 256, 256, 0, (cudaStream_t)a.stream>>>(a.workspace, a.n_chains);
+  sched_init_kernel<<<(a.n_chains + 255) / 256, 256, 0, (cudaStream_t)a.stream>>>(a.workspace, a.n_chains, a.n_trans);
   kern<<<(unsigned)grid, G, smem, (cudaStream_t)a.stream>>>(a, tgt, cfg);
   LMC_CUDA(cudaGetLastError());
   return LMC_OK;

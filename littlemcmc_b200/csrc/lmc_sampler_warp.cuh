@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
   //         chunk / doubling, after the chunk's table has been consumed): its first rows.  Totals land in vDot.
   TableGroup<LY::kRowLd> grp{lane, part + 2 * B * LY::kRowLd, vDot};
   TableGroup<LY::kRowLd> tgrp{lane, part, vDot};
-  const SchedView sv = sched_view(a.workspace, a.n_chains);
+  const SchedView sv = sched_view(a.workspace, a.n_chains, a.n_trans);
   const unsigned total_units = (unsigned)a.n_chains * (unsigned)a.n_trans;
 
   const int D = a.ndim;
@@ -690,7 +690,7 @@ int launch_warp_kernel(const void* kern, const lmc_sampler_args& a, const void* 
   const long long need = (long long)sched_bytes(a.n_chains) + grid * WPB * (long long)cfg.ws_vecs * VS * 16;
   if (need > a.workspace_bytes) return LMC_ERR_WORKSPACE;
   if ((long long)a.n_chains * a.n_trans >= (1ll << 31)) return LMC_ERR_UNSUPPORTED;
-  sched_init_kernel<<<(a.n_chains + 255) / 256, 256, 0, (cudaStream_t)a.stream>>>(a.workspace, a.n_chains);
+  sched_init_kernel<<<(a.n_chains + 255) / 256, 256, 0, (cudaStream_t)a.stream>>>(a.workspace, a.n_chains, a.n_trans);
   void* kargs[] = {const_cast<lmc_sampler_args*>(&a), const_cast<void*>(tgt), &cfg};
   LMC_CUDA(cudaLaunchKernel(kern, dim3((unsigned)grid), dim3(32 * WPB), kargs, smem, (cudaStream_t)a.stream));
   LMC_CUDA(cudaGetLastError());

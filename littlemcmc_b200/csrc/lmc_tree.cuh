@@ -189,15 +189,29 @@ __device__ __forceinline__ void merge_scalars(const StackScalars* ss, int lvl, C
 // One merge of _build_subtree at stack level lvl >= 1 (nuts.py:387-417): tree1 = stack entry `lvl`, tree2 = cur (left
 // edge momentum lp(k), p_sum ps(k), right edge momentum p(k)).  `u` is the uniform of logbern (:404), drawn by the
 // caller even when the merged tree turns.  Returns `turning`.
-template <int G, int NP, class Grp, class VarF, class PF, class LpF, class PsF, class SetPsF, class SetLpF, class UF>
+// BATCH: all of tree1's scratch words are loaded before anything is stored.  Scratch accesses are generic loads / stores
+// that the compiler must keep in program order (a store may alias the next load), so the plain form pays one dependent
+// L2 round trip per pair; kernels with the registers to hold 3 x NP pairs for a moment ask for the batched form.
+template <int G, int NP, bool BATCH = false, class Grp, class VarF, class PF, class LpF, class PsF, class SetPsF,
+          class SetLpF, class UF>
 __device__ __forceinline__ bool merge_upper(const Scratch<G, NP>& sc, Grp& grp, const StackScalars* ss, int lvl,
                                             VarF var, PF p, LpF lp, PsF ps, SetPsF set_ps, SetLpF set_lp, CurTree& cur,
                                             unsigned& free_slots, UF next_u) {
   double d6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  double2 b_lp[BATCH ? NP : 1], b_rp[BATCH ? NP : 1], b_ps[BATCH ? NP : 1];
+  if constexpr (BATCH) {
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      b_lp[k] = sc.ld(vid_stack(lvl, 0), k);
+      b_rp[k] = sc.ld(vid_stack(lvl, 1), k);
+      b_ps[k] = sc.ld(vid_stack(lvl, 2), k);
+    }
+  }
 #pragma unroll
   for (int k = 0; k < NP; ++k) {
-    const double2 t1_lp = sc.ld(vid_stack(lvl, 0), k), t1_rp = sc.ld(vid_stack(lvl, 1), k);
-    const double2 t1_ps = sc.ld(vid_stack(lvl, 2), k);
+    const double2 t1_lp = BATCH ? b_lp[BATCH ? k : 0] : sc.ld(vid_stack(lvl, 0), k);
+    const double2 t1_rp = BATCH ? b_rp[BATCH ? k : 0] : sc.ld(vid_stack(lvl, 1), k);
+    const double2 t1_ps = BATCH ? b_ps[BATCH ? k : 0] : sc.ld(vid_stack(lvl, 2), k);
     const double2 c_lp = lp(k), c_ps = ps(k), vk = var(k), pk = p(k);
     const double2 nps = add2(t1_ps, c_ps);   // p_sum = tree1.p_sum + tree2.p_sum (:390)
     const double2 ps1 = add2(t1_ps, c_lp);   // tree1.p_sum + tree2.left.p (:394)
@@ -341,13 +355,34 @@ __device__ __forceinline__ void push_cur(const Scratch<G, NP>& sc, StackScalars*
 
 // Top of _Tree.extend after a completed subtree T = cur (nuts.py:321-340): T.left.p = lp(k), T.right = z = (q, p),
 // T.p_sum = ps(k).  `u` is the uniform of the biased progressive accept (:321-323).  Returns `turning`.
-template <int G, int NP, class Grp, class VarF, class QF, class PF, class LpF, class PsF>
+// BATCH: as in merge_upper -- the old trajectory's words (and a proposal that moves) are loaded before anything is stored.
+template <int G, int NP, bool BATCH = false, class Grp, class VarF, class QF, class PF, class LpF, class PsF>
 __device__ __forceinline__ bool extend_top_f(const Scratch<G, NP>& sc, Grp& grp, int tail, int dir, VarF var, QF q,
                                              PF p, LpF lp, PsF ps, const CurTree& cur, TrajScalars& tr, double u) {
+  double2 b_ps[BATCH ? NP : 1], b_lp[BATCH ? NP : 1], b_rp[BATCH ? NP : 1];
+  if constexpr (BATCH) {
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      b_ps[k] = sc.ld(tvid(tail, T_PSUM), k);
+      b_lp[k] = sc.ld(tvid(tail, T_LP), k);
+      b_rp[k] = sc.ld(tvid(tail, T_RP), k);
+    }
+  }
   if (xf_u_less(u, xf_add(tr.Wp, xf_one()), cur.w)) {  // logbern(tree.log_size - self.log_size) :321-323
     tr.prop_E = cur.pE;
     tr.prop_logp = cur.plogp;
-    if (cur.pslot == kLeafProp) {
+    if constexpr (BATCH) {
+      double2 t[NP];
+      if (cur.pslot == kLeafProp) {
+#pragma unroll
+        for (int k = 0; k < NP; ++k) t[k] = q(k);
+      } else {
+#pragma unroll
+        for (int k = 0; k < NP; ++k) t[k] = sc.ld(vid_prop(cur.pslot), k);
+      }
+#pragma unroll
+      for (int k = 0; k < NP; ++k) sc.st(tvid(tail, T_PROPQ), k, t[k]);
+    } else if (cur.pslot == kLeafProp) {
 #pragma unroll
       for (int k = 0; k < NP; ++k) sc.st(tvid(tail, T_PROPQ), k, q(k));
     } else {
@@ -361,9 +396,10 @@ __device__ __forceinline__ bool extend_top_f(const Scratch<G, NP>& sc, Grp& grp,
 #pragma unroll
   for (int k = 0; k < NP; ++k) {
     const double2 c_ps = ps(k), c_lp = lp(k), vk = var(k), pk = p(k);
-    const double2 psum = add2(sc.ld(tvid(tail, T_PSUM), k), c_ps);  // self.p_sum[:] += tree.p_sum (:329)
+    const double2 psum = add2(BATCH ? b_ps[BATCH ? k : 0] : sc.ld(tvid(tail, T_PSUM), k), c_ps);  // self.p_sum[:] += tree.p_sum (:329)
     sc.st(tvid(tail, T_PSUM), k, psum);
-    const double2 oLp = sc.ld(tvid(tail, T_LP), k), oRp = sc.ld(tvid(tail, T_RP), k);  // old edges' momenta
+    const double2 oLp = BATCH ? b_lp[BATCH ? k : 0] : sc.ld(tvid(tail, T_LP), k);  // old edges' momenta
+    const double2 oRp = BATCH ? b_rp[BATCH ? k : 0] : sc.ld(tvid(tail, T_RP), k);
     const double2 voL = mul2(vk, oLp), voR = mul2(vk, oRp);
     const double2 vTl = mul2(vk, c_lp), vTr = mul2(vk, pk);
     if (dir > 0) {
@@ -495,6 +531,74 @@ __device__ __forceinline__ void welford_update(int lane, int D, int ldh, double*
         rfg[j] = r;
         mbg[j] = m2;
         rbg[j] = r2;
+      }
+    }
+  }
+  if (sw) {
+    ws.w_fg = ws.w_bg;
+    ws.w_bg = 0.0;
+    ws.window = (long long)((double)ws.window * window_multiplier);
+  }
+  ++ws.n_samples;
+}
+
+// The same update with every row loaded before anything is computed or stored (one HBM round trip for the four rows
+// instead of a dependent chain per pair): for kernels with the registers to hold 4 x NP pairs for a moment.  Identical
+// results.
+template <int G, int NP>
+__device__ __forceinline__ void welford_update_batched(int lane, int D, int ldh, double* mean_fg, double* rawvar_fg,
+                                                       double* mean_bg, double* rawvar_bg, const double2 (&q)[NP],
+                                                       double2 (&var)[NP], WelfordScalars& ws, double window_multiplier) {
+  double2* mfg = reinterpret_cast<double2*>(mean_fg);
+  double2* rfg = reinterpret_cast<double2*>(rawvar_fg);
+  double2* mbg = reinterpret_cast<double2*>(mean_bg);
+  double2* rbg = reinterpret_cast<double2*>(rawvar_bg);
+  double2 m[NP], r[NP], m2[NP], r2[NP];
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    const int j = lane + k * G;
+    const double2 z = make_double2(0.0, 0.0);
+    m[k] = j < ldh ? ldcg2(mfg + j) : z;
+    r[k] = j < ldh ? ldcg2(rfg + j) : z;
+    m2[k] = j < ldh ? ldcg2(mbg + j) : z;
+    r2[k] = j < ldh ? ldcg2(rbg + j) : z;
+  }
+  ws.w_fg += 1.0;
+  ws.w_bg += 1.0;
+  const double prop_fg = 1.0 / ws.w_fg, prop_bg = 1.0 / ws.w_bg;
+  const bool sw = ws.n_samples > 0 && ws.window > 0 && (ws.n_samples % ws.window) == 0;
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    double2 od = make_double2(add_rn(q[k].x, -m[k].x), add_rn(q[k].y, -m[k].y));  // old_diff = x - mean
+    m[k] = axpy2(m[k], prop_fg, od);                                            // mean += prop * old_diff
+    double2 nd = make_double2(add_rn(q[k].x, -m[k].x), add_rn(q[k].y, -m[k].y));  // new_diff = x - mean
+    r[k] = add2(r[k], mul2(od, nd));                                            // raw_var += old*new
+    od = make_double2(add_rn(q[k].x, -m2[k].x), add_rn(q[k].y, -m2[k].y));
+    m2[k] = axpy2(m2[k], prop_bg, od);
+    nd = make_double2(add_rn(q[k].x, -m2[k].x), add_rn(q[k].y, -m2[k].y));
+    r2[k] = add2(r2[k], mul2(od, nd));
+  }
+  div_pairs<NP>(r, ws.w_fg, var);  // _update_from_weightvar(fg) (:226-229)
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    const int j = lane + k * G;
+    if (2 * j >= D) var[k].x = 0.0;
+    if (2 * j + 1 >= D) var[k].y = 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    const int j = lane + k * G;
+    if (j < ldh) {
+      if (sw) {  // foreground <- background, background <- fresh (:240-243)
+        mfg[j] = m2[k];
+        rfg[j] = r2[k];
+        mbg[j] = make_double2(0.0, 0.0);
+        rbg[j] = make_double2(0.0, 0.0);
+      } else {
+        mfg[j] = m[k];
+        rfg[j] = r[k];
+        mbg[j] = m2[k];
+        rbg[j] = r2[k];
       }
     }
   }

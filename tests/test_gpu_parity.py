@@ -164,6 +164,31 @@ def test_warp_kernel_parity(name, chunk):
     pu.assert_parity(res, rtol=RTOL)
 
 
+CTA_CASES = ["nuts_illcond_d1000", "nuts_deep_d1000", "nuts_diag_d37", "nuts_static_d100", "nuts_funnel_d10",
+             "nuts_deep_d100", "nuts_deep_funnel_d50", "nuts_deep_funnel_d10", "nuts_early_gt_max_d20", "nuts_b1_d10"]
+
+
+@pytest.mark.parametrize("chunk", [2, 4])
+@pytest.mark.parametrize("name", CTA_CASES)
+def test_cta_kernel_parity(name, chunk):
+    """The chunked CTA-per-chain NUTS kernel (lmc_sampler_cta.cuh: 128 threads per chain, the default for 513..1024
+    dimensions; forced here with group=2 for every fixture) for both chunk lengths, with the tree scratch in the global
+    workspace and as much of it in shared memory as fits, sticky and through the FIFO scheduler."""
+    for smem in (0, -1):
+        res = pu.run_case_on_gpu_and_oracle(name, knobs=dict(group=2, chunk=chunk, smem_vecs=smem))
+        pu.assert_parity(res, rtol=RTOL)
+    # fewer resident CTAs than chains: the FIFO scheduler instead of the sticky chain -> CTA assignment
+    res = pu.run_case_on_gpu_and_oracle(name, knobs=dict(group=2, chunk=chunk, max_slots=1))
+    pu.assert_parity(res, rtol=RTOL)
+
+
+def test_cta_kernel_occupancy_variants():
+    """chunk of 2 with three / four resident CTAs per SM (group 203 / 204): same results"""
+    for group in (203, 204):
+        res = pu.run_case_on_gpu_and_oracle("nuts_illcond_d1000", knobs=dict(group=group, chunk=2))
+        pu.assert_parity(res, rtol=RTOL)
+
+
 @pytest.mark.parametrize("name", ["nuts_diag_d37", "nuts_funnel_d10"])
 def test_warp_kernel_agrees_with_the_one_warp_register_kernel(name):
     """Chained adaptive runs of the chunked kernel and of the round-1 one-warp kernel (group=32): same decisions, floats

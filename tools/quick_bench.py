@@ -1,5 +1,5 @@
 """Scratch throughput probe (not the contract bench): NUTS with in-kernel Philox, sweeping launch knobs.
-Usage: python tools/quick_bench.py C D n_trans [groups] [smems] [slots] [chunks] [target=gauss|funnel] [depth]
+Usage: python tools/quick_bench.py C D n_trans [groups] [smems] [slots] [chunks] [target=gauss|funnel] [depth] [warm] [early_depth]
 (lists are comma separated; group 0 = library default, 1 = chunked warp kernel, >= 32 register kernel, < 0 lean)"""
 import sys
 
@@ -21,6 +21,7 @@ chunks = [int(x) for x in arg[6].split(",")] if len(arg) > 6 else [0]
 target = arg[7] if len(arg) > 7 else "gauss"
 depth = int(arg[8]) if len(arg) > 8 else 10
 warm = int(arg[9]) if len(arg) > 9 else 100
+early = int(arg[10]) if len(arg) > 10 else 8   # early_max_treedepth (the cap while iteration < 200)
 
 dev = "cuda:0"
 if target == "funnel":
@@ -29,7 +30,7 @@ else:
     sigma = 10 ** np.linspace(-0.5, 0.5, D)
     tgt = engine.FusedTarget(L.TARGET_DIAG_GAUSSIAN, D, tau=1 / sigma**2)
 params = dict(adapt_mass=1, adapt_step_size=1, target_accept=0.8, gamma=0.05, k=0.75, t0=10, Emax=1000.0,
-              max_treedepth=depth, early_max_treedepth=8)
+              max_treedepth=depth, early_max_treedepth=early)
 seeds = engine.seeds_tensor(np.arange(C) + 12345, dev)
 for g in groups:
     for sm in smems:
