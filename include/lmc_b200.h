@@ -332,6 +332,10 @@ int lmc_callback_loop_destroy(lmc_callback_loop* loop);
 #define LMC_NEED_VEL 2
 #define LMC_NEED_MOM 4
 #define LMC_NEED_UPDATE 8
+/* IN (set by the caller in need[chain] before lmc_dense_advance): "not served yet" -- the chain is left exactly where it
+ * is and keeps its request.  A caller whose potential.update is expensive per CALL rather than per chain (one batched
+ * Cholesky for any number of matrices) holds the chains that ask for it until enough of them wait. */
+#define LMC_NEED_HOLD 16
 
 typedef struct lmc_dense_args {
   lmc_sampler_args base;
@@ -342,7 +346,7 @@ typedef struct lmc_dense_args {
   const double* v_eval;    /* [n_chains, 2, ld] in : velocity(x_eval rows)                                         */
   double* n_eval;          /* [n_chains, ld]    out: standard normals of the next momentum draw                    */
   const double* p0_eval;   /* [n_chains, ld]    in : potential.random() for those normals                          */
-  int32_t* need;           /* [n_chains]        out: OR of LMC_NEED_* the chain waits for (0: finished)            */
+  int32_t* need;           /* [n_chains]        out: OR of LMC_NEED_* the chain waits for (0: finished); in: HOLD   */
   void* machine;           /* >= lmc_dense_state_bytes(...) bytes, 16-byte aligned, owned by the caller            */
   int64_t machine_bytes;
   int32_t* n_running;      /* device counter: chains that have not finished                                        */

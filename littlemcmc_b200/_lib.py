@@ -65,7 +65,7 @@ class DenseArgs(C.Structure):
                 ("need", C.c_void_p), ("machine", C.c_void_p), ("machine_bytes", C.c_int64), ("n_running", C.c_void_p)]
 
 
-NEED_GRAD, NEED_VEL, NEED_MOM, NEED_UPDATE = 1, 2, 4, 8
+NEED_GRAD, NEED_VEL, NEED_MOM, NEED_UPDATE, NEED_HOLD = 1, 2, 4, 8, 16
 
 # every symbol include/lmc_b200.h declares: (restype, argtypes)
 _P, _I32, _I64 = C.c_void_p, C.c_int32, C.c_int64

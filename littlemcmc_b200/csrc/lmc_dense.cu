@@ -254,6 +254,8 @@ __global__ void __launch_bounds__(dn_block<G>()) dn_advance_kernel(const lmc_den
   const int chain = blockIdx.x * CPB + gib;
   if (chain >= a.n_chains) return;
   DnMachine* const M = reinterpret_cast<DnMachine*>(reinterpret_cast<char*>(c.machine) + (size_t)chain * kDnMachineBytes);
+  // the caller has not served this chain yet (it batches potential.update over chains): nothing moves, need stays
+  if (c.need[chain] & LMC_NEED_HOLD) return;
   DnScalars s = M->s;
   if (s.phase == DPH_DONE) {  // a finished chain may still have asked for its last potential.update: served by now
     if (lane == 0) c.need[chain] = 0;

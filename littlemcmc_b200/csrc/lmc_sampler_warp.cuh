@@ -94,6 +94,20 @@ struct TableGroup {
   }
 };
 
+// LMC_WARP_TIMING: lane 0 of every CTA's first warp accumulates clock64() deltas per phase (index = the phase that just
+// ENDED) and block 0 prints its totals -- a development probe (-DLMC_WARP_TIMING=1 variant build, tools/quick_bench.py)
+#ifdef LMC_WARP_TIMING
+#include <stdio.h>
+#define LMC_WTICK(i)                                 \
+  if (threadIdx.x == 0) {                            \
+    const long long now_ = clock64();                \
+    s_tacc[i] += now_ - s_tacc[15];                  \
+    s_tacc[15] = now_;                               \
+  }
+#else
+#define LMC_WTICK(i)
+#endif
+
 template <class Target, int NP, int B, int WPB, int MINB, bool TAPE>
 __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_sampler_args a, const Target tgt,
                                                                       const WarpCfg cfg) {
@@ -158,6 +172,13 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
     return (s0 + s1) + (s2 + s3);
   };
 
+#ifdef LMC_WARP_TIMING
+  __shared__ long long s_tacc[16];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 15; ++i) s_tacc[i] = 0;
+    s_tacc[15] = clock64();
+  }
+#endif
   // "sticky" launches: when every chain has its own resident warp there is nothing to schedule -- warp `slot` runs all
   // the transitions of chain `slot` back to back, position and mass matrix stay on chip, and the FIFO's atomics, fences
   // and state reloads (3 dependent L2 round trips + 2 membars per transition) disappear.  Same results either way.
@@ -180,6 +201,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
       t = __shfl_sync(FULL, t, 0);
     }
     if (chain == -1) break;
+    LMC_WTICK(0);
     bool dead = ((unsigned)chain & kDeadBit) != 0u;
     chain &= 0x7fffffff;
     const size_t row = (size_t)chain * a.n_trans + t;
@@ -243,6 +265,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
         }
       }
 
+      LMC_WTICK(1);
       // ---- start = integrator.compute_state(q0, p0)  (integration.py:52-66) ----------------------------------------
       double E0, logp0;
       {
@@ -274,6 +297,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
         tree_init<G, NP>(sc, tail, q, p, g);
         reached_max = max_depth <= 0;
         for (int d = 0; d < max_depth; ++d) {  // nuts.py:212
+          LMC_WTICK(2);
           const int dir = (next_uniform() < 0.5) ? 1 : -1;
           if (reg_edge != 0 && reg_edge != dir) {
             const int eb = (dir > 0 ? T_RQ : T_LQ);
@@ -297,6 +321,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
           int pidx = 0;  // ring index of cur's proposal while cur.pslot == kLeafProp ("still in the position ring")
 
           for (unsigned c = 0; c < n_chunks && !fail; ++c) {
+            LMC_WTICK(3);
             // ---- 1. Bc leapfrogs (integration.py:100-121), no reduction between them ------------------------------------
             for (int s = 0; s < Bc; ++s) {
               double pre[2] = {0.0, 0.0};
@@ -325,6 +350,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
               *skew(s) = k_part;
               *skew(B + s) = lp_part;
             }
+            LMC_WTICK(4);
             // ---- 2. dot products of the merges inside the chunk (nuts.py:387-398), every lane on its own columns ------------
             if (Bc >= 2) {
               for (int k2 = 0; k2 < Bc / 2; ++k2) {  // level 0: two leaves
@@ -374,6 +400,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
                 row0 += 6 * n_m;
               }
             }
+            LMC_WTICK(5);
             __syncwarp();
             // ---- 3. one transposed reduction: lane r sums row r ---------------------------------------------------------------
             {
@@ -427,6 +454,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
               }
               turnmask = __ballot_sync(FULL, flag);
             }
+            LMC_WTICK(6);
             // ---- 4. the chunk's leaves and merges in the reference's post-order (uniform across the warp) -------------------
             for (int s = 0; s < Bc; ++s) {
               ++n_leaves;
@@ -479,6 +507,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
               }
             }
             if (fail) break;
+            LMC_WTICK(7);
             // ---- 5. the chunk is a subtree of level bc: merge it with the stack levels >= bc (generic path) -------------------
             if (n_chunks > 1) {
               double2 var[NP], cur_lp[NP], cur_ps[NP];
@@ -533,6 +562,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
                 }
               }
             }
+            LMC_WTICK(8);
           }
           ++tr.depth;            // nuts.py:315
           tr.n_prop += n_leaves;  // :316
@@ -540,6 +570,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
             diverging = (fail == 1);
             break;
           }
+          LMC_WTICK(8);
           // ---- top of _Tree.extend (nuts.py:321-340): T.left.p = ring_p[0] (or p), T.p_sum = psbuf[0] (or p) ------------------
           {
             double2 var[NP], cur_lp[NP], cur_ps[NP], qprop[NP];
@@ -559,6 +590,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
                                     PairArray<NP>{cur_lp}, PairArray<NP>{cur_ps}, cur, tr, next_uniform()))
               break;  // :340
           }
+          LMC_WTICK(9);
           if (d + 1 < max_depth) {
             const int eb = (dir > 0 ? T_RQ : T_LQ);
 #pragma unroll
@@ -572,6 +604,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
             reached_max = true;
           }
         }
+        LMC_WTICK(10);
         const double accept_stat = mean_tree_accept(tr);
 #pragma unroll
         for (int k = 0; k < NP; ++k) q[k] = sc.ld(tvid(tail, T_PROPQ), k);  // hmc_step.end.q
@@ -653,7 +686,15 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
       if (lane == 0 && completes_block(a, t)) report_block(a, t);
       if (lane == 0 && t + 1 < a.n_trans) sched_push(sv, (unsigned)a.n_chains, chain, t + 1, dead);
     }
+    LMC_WTICK(11);
   }
+#ifdef LMC_WARP_TIMING
+  if (threadIdx.x == 0 && blockIdx.x == 0)
+    printf("warp-timing kcycles: pop %lld load+draw %lld init|edgesave %lld dir+reload %lld leap %lld dots %lld reduce %lld "
+           "scalar %lld merge %lld extend %lld exit %lld epilogue+push %lld\n", s_tacc[0] / 1000, s_tacc[1] / 1000,
+           s_tacc[2] / 1000, s_tacc[3] / 1000, s_tacc[4] / 1000, s_tacc[5] / 1000, s_tacc[6] / 1000, s_tacc[7] / 1000,
+           s_tacc[8] / 1000, s_tacc[9] / 1000, s_tacc[10] / 1000, s_tacc[11] / 1000);
+#endif
 }
 
 #ifndef __CUDACC_RTC__

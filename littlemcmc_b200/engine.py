@@ -565,6 +565,7 @@ class DenseRun:
         self.n_eval, self.p0_eval = z(Cn, ld), z(Cn, ld)
         self.need = torch.zeros(Cn, dtype=torch.int32, device=dev)
         self.need_host = torch.zeros(Cn, dtype=torch.int32).pin_memory()
+        self._need_stage = torch.zeros(Cn, dtype=torch.int32).pin_memory()   # need + HOLD marks on their way back
         # index lists travel through pinned staging (a pageable H2D copy blocks the host for tens of microseconds)
         self._idx_pinned = [torch.zeros(Cn, dtype=torch.int64).pin_memory() for _ in range(4)]
         self._idx_dev = [torch.zeros(Cn, dtype=torch.int64, device=dev) for _ in range(4)]
@@ -619,10 +620,29 @@ class DenseRun:
                 need = self.need_host.numpy()
                 if not need.any():
                     break
-                m_upd, m_mom = (need & L.NEED_UPDATE) != 0, (need & L.NEED_MOM) != 0
-                m_grad, m_vel = (need & L.NEED_GRAD) != 0, (need & L.NEED_VEL) != 0
+                m_upd = (need & L.NEED_UPDATE) != 0
                 if m_upd.any():                           # potential.update first: the momentum draw uses the new matrix
-                    pot._update_rows(torch.as_tensor(np.nonzero(m_upd)[0], device=dev), self.chains.q)
+                    # An adapted dense matrix is refactored after every tuning sample (quadpotential.py:520-526), and a
+                    # batched Cholesky costs the same ~10 ms for 8 matrices as for 256: chains that ask for their update
+                    # are HELD (LMC_NEED_HOLD: the kernel leaves them where they are) until a quarter of the chains
+                    # still running wait for one, or nobody is left in the middle of a trajectory.
+                    busy = ((need & (L.NEED_GRAD | L.NEED_VEL)) != 0) & ~m_upd
+                    batch = float(getattr(pot, "_update_batch_fraction", 0.0))
+                    if busy.any() and m_upd.sum() < batch * ((need & ~L.NEED_HOLD) != 0).sum():
+                        if (need[m_upd] & L.NEED_HOLD).all():
+                            pass                          # all of them are marked already
+                        else:
+                            self._need_stage.numpy()[:] = need
+                            self._need_stage.numpy()[m_upd] |= L.NEED_HOLD
+                            self.need.copy_(self._need_stage, non_blocking=True)
+                        need = need & ~np.where(m_upd, L.NEED_GRAD | L.NEED_MOM | L.NEED_UPDATE, 0).astype(need.dtype)
+                    else:
+                        pot._update_rows(torch.as_tensor(np.nonzero(m_upd)[0], device=dev), self.chains.q)
+                        if (need[m_upd] & L.NEED_HOLD).any():
+                            self._need_stage.numpy()[:] = need & ~np.where(m_upd, L.NEED_HOLD, 0).astype(need.dtype)
+                            self.need.copy_(self._need_stage, non_blocking=True)
+                m_mom = (need & L.NEED_MOM) != 0
+                m_grad, m_vel = (need & L.NEED_GRAD) != 0, (need & L.NEED_VEL) != 0
                 self._idx_slot = 0
                 lib_all = float(getattr(pot, "_all_rows_above", 1.0))
                 if m_mom.any():

@@ -190,6 +190,9 @@ class QuadPotentialFullAdapt(_DenseBase):
     per chain."""
 
     _adaptive = True
+    # engine.DenseRun holds chains that ask for their update until this fraction of the running chains waits for one
+    # (one batched Cholesky costs the same for 8 matrices as for 256); 0 = serve every request at once
+    _update_batch_fraction = 0.25
 
     def __init__(self, n, initial_mean, initial_cov=None, initial_weight=0, adaptation_window=101,
                  adaptation_window_multiplier=2, update_window=1, dtype=None):
@@ -224,6 +227,7 @@ class QuadPotentialFullAdapt(_DenseBase):
         self._raw_fg, self._raw_bg = z(self._nc, D, lda), z(self._nc, D, lda)
         self._mean_fg, self._mean_bg = z(self._nc, ld), z(self._nc, ld)
         self._nsamp = z(self._nc, 2)
+        self._work = None                              # gather / factor buffers of _update_rows, allocated on first use
         self._reset_state()
 
     def _reset_state(self):
@@ -282,7 +286,13 @@ class QuadPotentialFullAdapt(_DenseBase):
     def _momentum_rows(self, idx, n_eval, p0_eval):
         D = self._n
         ns = n_eval[:, :D] if idx is None else n_eval[idx][:, :D]
-        chol = self._chol_all if idx is None else self._chol_all[idx]
+        if idx is None:
+            chol = self._chol_all
+        else:                                   # gathered into the long-lived work buffer (see _update_rows)
+            if self._work is None:
+                self._work = (torch.empty_like(self._cov_all), torch.empty_like(self._chol_all),
+                              torch.empty(self._nc, dtype=torch.int32, device=self._dev))
+            chol = torch.index_select(self._chol_all, 0, idx, out=self._work[1][:int(idx.numel())])
         ps = torch.linalg.solve_triangular(chol.mT, ns[:, :, None], upper=True)[:, :, 0]   # :455-456 per chain
         if idx is None:
             p0_eval[:, :D] = ps
@@ -309,11 +319,22 @@ class QuadPotentialFullAdapt(_DenseBase):
                                              _ptr(self._cov_all) if flag else None, stream), "lmc_dense_cov_update")
             sel32.record_stream(torch.cuda.current_stream(self._dev))
             if flag:                                                      # _update_from_weightvar (:520-526)
-                chol, info = torch.linalg.cholesky_ex(self._cov_all[sel][:, :, :D])
-                ok = (info == 0) & torch.isfinite(chol).all(dim=2).all(dim=1)   # LinAlgError / ValueError in scipy (:524)
-                if not bool(ok.all()):
+                # gather -> factor -> scatter through two work buffers that live as long as the potential: the batch
+                # changes from call to call, and fresh [k, D, D] temporaries of a new size every time are a cudaMalloc
+                # (and eventually a synchronising cudaFree) each -- measured 22 ms per call instead of 8
+                k = int(sel.numel())
+                if self._work is None:
+                    self._work = (torch.empty_like(self._cov_all), torch.empty_like(self._chol_all),
+                                  torch.empty(self._nc, dtype=torch.int32, device=self._dev))
+                wa, wl, winfo = (w[:k] for w in self._work)
+                torch.index_select(self._cov_all, 0, sel, out=wa)
+                chol, info = torch.linalg.cholesky_ex(wa[:, :, :D], out=(wl, winfo))
+                ok = (info == 0) & torch.isfinite(chol.sum(dim=(1, 2)))      # LinAlgError / ValueError in scipy (:524)
+                if bool(ok.all()):
+                    self._chol_all.index_copy_(0, sel, chol)
+                else:
                     self._chol_error = "Cholesky failed for chain(s) %s" % sel[~ok].tolist()[:8]
-                self._chol_all[sel[ok]] = chol[ok]
+                    self._chol_all[sel[ok]] = chol[ok]
         switch = idx_h[delta >= self._window_all[idx_h]]                 # :545-552
         if switch.size:
             sw = torch.as_tensor(switch, device=self._dev)

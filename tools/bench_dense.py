@@ -75,6 +75,9 @@ for name, mk, n_trans, tune in (("QuadPotentialFull (shared matrix)", lambda: lm
                                 ("QuadPotentialFullAdapt (per-chain matrix)",
                                  lambda: lmc.QuadPotentialFullAdapt(D, np.zeros(D), np.eye(D), 10), 12, 12)):
     chains = Cn if "shared" in name else min(Cn, 256)
+    # warm-up call: library handles (cuBLAS, cuSOLVER), allocator pools, first-launch costs
+    lmc.sample(target, D, draws=0, tune=2, step=lmc.NUTS(target, D, potential=mk(), max_treedepth=8), chains=chains,
+               start=np.zeros(D), random_seed=list(range(chains)), discard_tuned_samples=False, return_device=True)
     step = lmc.NUTS(target, D, potential=mk(), max_treedepth=8)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
