@@ -166,12 +166,13 @@ typedef struct lmc_sampler_args {
   int64_t workspace_bytes;
   void* stream;        /* cudaStream_t                                                                      */
   int32_t tune_group;  /* 0 = library picks the kernel and threads-per-chain; 1: force the chunked warp-per-chain
-                          NUTS kernel (ndim <= 256); >= 32: force 32/64/128/256/512/1024 threads per chain with the
-                          register-resident kernel; < 0: force -tune_group (64/128/256) with the lean NUTS kernel
-                          (experiments and tests)                                                            */
+                          NUTS kernel (ndim <= 256); 2: force the chunked CTA-per-chain NUTS kernel (128 threads per
+                          chain, ndim <= 1024; 203 / 204: with 3 / 4 resident CTAs per SM); >= 32 otherwise: force
+                          32/64/128/256/512/1024 threads per chain with the register-resident kernel; < 0: force
+                          -tune_group (64/128/256) with the lean NUTS kernel (experiments and tests)          */
   int32_t tune_smem_vecs; /* -1 = library picks how many scratch vectors live in shared memory; else force  */
   int32_t tune_max_slots; /* 0 = library picks the number of resident chain slots; else cap it              */
-  int32_t tune_chunk;  /* chunked warp kernel: leaves per chunk (2, 4, 8, 16); 0 = library picks            */
+  int32_t tune_chunk;  /* chunked kernels: leaves per chunk (warp: 2, 4, 8, 16; CTA: 2, 4); 0 = library picks    */
 
   /* One launch for a whole run with a host-resident trace (ABI v3; fused and user-target kernels only, the callback and
    * dense state machines require 0 / NULL).  The reference discards tuning draws after the fact (sampling.py:473-476)

@@ -226,3 +226,36 @@ def test_full_adapt_object_api_like_the_reference_tests():
         pot.update(np.ones(2), None, True)
     with pytest.raises(ValueError):
         pot.raise_ok(None)
+
+
+def test_held_updates_give_the_same_chains():
+    """engine.DenseRun holds chains that ask for potential.update until enough of them wait (LMC_NEED_HOLD, one batched
+    Cholesky per group instead of one per straggler).  Every chain only ever uses its own matrix, so the draws must not
+    depend on the batching policy: serve-at-once (fraction 0), the default quarter, and wait-for-everybody (fraction 1)
+    take the same tree decisions and agree to rounding -- not bit for bit: the batched Cholesky picks its algorithm by
+    batch size, so a factor differs in the last bits with the company it is computed in (the run is kept short, the
+    chaotic feedback of adaptation amplifies such differences like any other, tests/test_gpu_parity.py)."""
+    import torch
+    import littlemcmc_b200 as lmc
+    D = 24
+    prec = du.spd(D, 3)
+    P = torch.as_tensor(prec, device="cuda")
+
+    def fn(q):
+        g = -(q @ P)
+        return 0.5 * (q * g).sum(1), g
+
+    target = lmc.targets.TorchBatched(fn)
+    out = []
+    for frac in (0.0, 0.25, 1.0):
+        pot = lmc.QuadPotentialFullAdapt(D, np.zeros(D), np.eye(D), 10, adaptation_window=20)
+        pot._update_batch_fraction = frac
+        step = lmc.NUTS(target, D, potential=pot, max_treedepth=6)
+        tr, st = lmc.sample(target, D, draws=2, tune=6, step=step, chains=32, start=np.zeros(D),
+                            random_seed=list(range(32)), discard_tuned_samples=False)
+        out.append((tr, st))
+    for tr, st in out[1:]:
+        assert np.array_equal(st["tree_size"], out[0][1]["tree_size"])
+        assert np.array_equal(st["depth"], out[0][1]["depth"])
+        np.testing.assert_allclose(tr, out[0][0], rtol=1e-8, atol=1e-10)
+    assert out[0][1]["depth"].std() > 0, "the chains must not move in lock step for this test to mean anything"
