@@ -94,6 +94,11 @@ struct TableGroup {
   }
 };
 
+// LMC_WARP_LANE_TREE 1 (default): the scalar pass over a chunk is resolved by all lanes at once (phase 4 below);
+// 0: the sequential walk in the reference's post-order (kept for comparison: same results)
+#ifndef LMC_WARP_LANE_TREE
+#define LMC_WARP_LANE_TREE 1
+#endif
 // LMC_WARP_TIMING: lane 0 of every CTA's first warp accumulates clock64() deltas per phase (index = the phase that just
 // ENDED) and block 0 prints its totals -- a development probe (-DLMC_WARP_TIMING=1 variant build, tools/quick_bench.py)
 #ifdef LMC_WARP_TIMING
@@ -402,6 +407,149 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
             }
             LMC_WTICK(5);
             __syncwarp();
+#if LMC_WARP_LANE_TREE
+            // ---- 3. one transposed reduction: lane r sums row r ---------------------------------------------------------------
+            double lE = 0.0, lLogp = 0.0, ldE = 0.0;  // the leaf of this lane (lane < Bc)
+            XF lw = xf_zero();
+            {
+              // energies: rows s (kinetic) and B + s (log-density sums), s < Bc
+              double sum = 0.0;
+              if (lane < Bc || (lane >= B && lane < B + Bc)) sum = row_sum(lane);
+              const double lp_s = __shfl_sync(FULL, sum, (lane + B) & 31);
+              if (lane < Bc) {
+                double pre[2] = {0.0, 0.0};
+                if constexpr (Target::kPre > 0) {
+                  pre[0] = vPre[2 * lane];
+                  pre[1] = vPre[2 * lane + 1];
+                }
+                lLogp = tgt.finish(lp_s, pre);
+                lE = 0.5 * sum - lLogp;
+                ldE = lE - E0;                               // nuts.py:352
+                if (isnan(ldE)) ldE = CUDART_INF;            // :353-354
+                if (fabs(ldE) < a.Emax) lw = xf_exp(-ldE);   // log_size = -dE (:359)
+              }
+              // merge dot products: rows 2B .. 2B + 4 Bc - 7
+              const int n_dot = Bc >= 2 ? 4 * Bc - 6 : 0;
+              for (int r = lane; r < n_dot; r += 32) vDot[r] = row_sum(2 * B + r);
+            }
+            __syncwarp();
+            // the merge this lane answers for (lane < Bc - 1): level ml, index midx, its U-turn flag
+            bool mflag = false;
+            int ml = 0, midx = 0;
+            if (lane < Bc - 1) {
+              int cnt = Bc / 2;
+              midx = lane;
+              while (midx >= cnt) {
+                midx -= cnt;
+                cnt >>= 1;
+                ++ml;
+              }
+              if (ml == 0) {
+                mflag = (vDot[2 * midx] <= 0) || (vDot[2 * midx + 1] <= 0);  // :391
+              } else {
+                int r0 = Bc;  // first row of level ml
+                for (int ll = 1; ll < ml; ++ll) r0 += 6 * (Bc >> (ll + 1));
+                const double* dd = vDot + r0 + 6 * midx;
+                mflag = (dd[0] <= 0) || (dd[1] <= 0) || (dd[2] <= 0) || (dd[3] <= 0) || (dd[4] <= 0) || (dd[5] <= 0);  // :391-398
+              }
+            }
+            LMC_WTICK(6);
+            // ---- 4. the chunk's leaves and merges, resolved by all lanes at once -----------------------------------------------
+            // The reference walks them in post-order (leaf 0, leaf 1, merge(0,1), leaf 2, ...) and stops at the first
+            // diverging leaf or turning merge.  Event numbers in that order: leaf s -> 2s - popc(s); the merge at level l
+            // completed by leaf i -> number(i) + 1 + l; its uniform is number i - popc(i) + l of the chunk.  So: the first
+            // failing event is a warp minimum, what the walk would have counted up to it are ballots, and without a failure
+            // the chunk's subtree is a log2(Bc)-step tree over lanes -- same values, same uniforms, same decisions.
+            {
+              const unsigned kNone = 0xffffffffu;
+              const unsigned ulane = (unsigned)lane;
+              const unsigned seq_leaf = 2u * ulane - (unsigned)__popc(ulane);
+              const unsigned m_i = ((unsigned)(midx + 1) << (ml + 1)) - 1u;  // leaf that completes this lane's merge
+              const unsigned m_rank = m_i - (unsigned)__popc(m_i) + (unsigned)ml;
+              const unsigned seq_merge = m_i + m_rank + 1u;                    // = 2 m_i - popc(m_i) + 1 + ml
+              const bool leaf_bad = lane < Bc && !(fabs(ldE) < a.Emax);      // :358 / :370-375
+              unsigned my = leaf_bad ? seq_leaf : kNone;
+              if (lane < Bc - 1 && mflag && seq_merge < my) my = seq_merge;
+              const unsigned F = __reduce_min_sync(FULL, my);
+              const bool leaf_in = lane < Bc && seq_leaf <= F;        // leaves the walk reaches
+              const bool merge_in = lane < Bc - 1 && seq_merge <= F;  // merges it completes (a turning one draws its uniform)
+              n_leaves += __popc(__ballot_sync(FULL, leaf_in));
+              const unsigned n_u = (unsigned)__popc(__ballot_sync(FULL, merge_in));
+              {  // max_energy_change over those leaves: the first one with the largest |dE| (:356-357)
+                const unsigned long long key = leaf_in ? (unsigned long long)__double_as_longlong(fabs(ldE)) : 0ull;
+                const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+                const unsigned mh = __reduce_max_sync(FULL, hi);
+                const unsigned mlo = __reduce_max_sync(FULL, (leaf_in && hi == mh) ? lo : 0u);
+                const unsigned who = __ballot_sync(FULL, leaf_in && hi == mh && lo == mlo);
+                const double cand = __shfl_sync(FULL, ldE, __ffs(who) - 1);
+                if (fabs(cand) > fabs(tr.max_dE)) tr.max_dE = cand;
+              }
+              const unsigned uc0 = uc;
+              if constexpr (TAPE) {
+                if (__any_sync(FULL, merge_in && (long long)(uc0 + m_rank) >= a.rng.u_stride)) status |= LMC_STATUS_TAPE_EXHAUSTED;
+              }
+              if (F != kNone) {
+                uc = uc0 + n_u;
+                fail = __ballot_sync(FULL, leaf_bad && seq_leaf == F) ? 1 : 2;
+                break;
+              }
+              // uniforms uc0 .. uc0 + Bc - 2 of this transition's stream
+              const unsigned blk = uc0 & ~31u;
+              double u_lo = 0.0, u_hi = 0.0;
+              if constexpr (!TAPE) {
+                if (Bc >= 2) {
+                  if ((uc0 & 31u) == 0u) u_lane = philox_uniform_cold(seed, it, uc0 + ulane);  // the block starts here
+                  u_lo = u_lane;
+                  if (uc0 + (unsigned)Bc - 2u >= blk + 32u) u_hi = philox_uniform_cold(seed, it, blk + 32u + ulane);
+                }
+              }
+              auto chunk_uniform = [&](unsigned r) -> double {  // called by all lanes
+                const unsigned x = uc0 + r;
+                if constexpr (TAPE) {
+                  return (long long)x < a.rng.u_stride ? a.rng.uniforms[row * a.rng.u_stride + x] : 0.5;
+                } else {
+                  const double ua = __shfl_sync(FULL, u_lo, (int)(x & 31u)), ub = __shfl_sync(FULL, u_hi, (int)(x & 31u));
+                  return x >= blk + 32u ? ub : ua;
+                }
+              };
+              // every group of Bc lanes builds the same tree: lane L starts from leaf L mod Bc
+              const int src = lane & (Bc - 1);
+              XF nw{__shfl_sync(FULL, lw.m, src), __shfl_sync(FULL, lw.e, src)};
+              const double sdE = __shfl_sync(FULL, ldE, src);
+              XF na = (-sdE < 0.0) ? xf_sqr(nw) : nw;  // log_p_accept_weighted = -dE + min(0, -dE)  (:363)
+              double npE = __shfl_sync(FULL, lE, src), nplogp = __shfl_sync(FULL, lLogp, src);
+              int npidx = src;
+              for (int l = 0; l < bc; ++l) {
+                const int bit = 1 << l;
+                const XF pw{__shfl_xor_sync(FULL, nw.m, bit), __shfl_xor_sync(FULL, nw.e, bit)};
+                const XF pa{__shfl_xor_sync(FULL, na.m, bit), __shfl_xor_sync(FULL, na.e, bit)};
+                const double ppE = __shfl_xor_sync(FULL, npE, bit), pplogp = __shfl_xor_sync(FULL, nplogp, bit);
+                const int ppidx = __shfl_xor_sync(FULL, npidx, bit);
+                const bool right = (lane & bit) != 0;  // this lane's node is tree2 of the merge
+                const XF t2w = right ? nw : pw;
+                const unsigned i_done = ((((unsigned)src >> (l + 1)) + 1u) << (l + 1)) - 1u;
+                const double u = chunk_uniform(i_done - (unsigned)__popc(i_done) + (unsigned)l);
+                const XF sw = xf_add(right ? pw : nw, t2w);         // log_size = logaddexp(...)            (:400)
+                const XF sa = xf_add(right ? pa : na, right ? na : pa);  // log_weighted_accept_sum          (:401-403)
+                const bool mine = xf_u_less(u, sw, t2w) == right;   // logbern(tree2.log_size - log_size)   (:404)
+                npE = mine ? npE : ppE;
+                nplogp = mine ? nplogp : pplogp;
+                npidx = mine ? npidx : ppidx;
+                nw = sw;
+                na = sa;
+              }
+              cur.w = nw;
+              cur.a = na;
+              cur.pE = npE;
+              cur.plogp = nplogp;
+              cur.pslot = kLeafProp;
+              pidx = npidx;
+              uc = uc0 + (unsigned)Bc - 1u;
+              if constexpr (!TAPE) {
+                if (Bc >= 2 && uc > blk + 32u) u_lane = u_hi;  // the stream continues in the next block of 32
+              }
+            }
+#else
             // ---- 3. one transposed reduction: lane r sums row r ---------------------------------------------------------------
             {
               // energies: rows s (kinetic) and B + s (log-density sums), s < Bc
@@ -506,6 +654,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
                 __syncwarp();
               }
             }
+#endif
             if (fail) break;
             LMC_WTICK(7);
             // ---- 5. the chunk is a subtree of level bc: merge it with the stack levels >= bc (generic path) -------------------
