@@ -14,9 +14,10 @@
 //      from the ring, every lane on its own columns, partials into the same table;
 //   3. ONE transposed reduction: lane r sums row r of the table (no shuffles), energies -> exp() on B lanes in
 //      parallel, U-turn flags -> one ballot;
-//   4. one scalar pass over the chunk in the reference's post-order (uniform across the warp, same uniforms in the same
-//      order as the recursion, stops at the first divergence / turn: leaves after it are discarded, and were the only
-//      wasted work);
+//   4. the chunk's leaves and merges are resolved by all lanes at once: the first failing event (diverging leaf, turning
+//      merge) in the reference's post-order is a warp minimum over closed-form event numbers, the subtree of a chunk
+//      without one is a log2(B)-step tree over lanes (same uniforms in the same order as the recursion; the leaves after
+//      a failure are discarded, and were the only wasted work);
 //   5. the chunk's subtree (level b) is merged with the stack levels >= b exactly as before (lmc_tree.cuh merge_level,
 //      vectors in the L2-resident workspace: touched once per B leaves).
 // Same arithmetic per element and the same decisions as the reference; dot products are summed in a fixed but
