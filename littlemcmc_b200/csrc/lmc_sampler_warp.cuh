@@ -56,7 +56,9 @@ struct WarpLayout {
   static constexpr int oInts = oVal + nValD * 8;
   static constexpr int nInts = B + 3 * (kLog + 1) + 1;
   static constexpr int oSS = ((oInts + nInts * 4) + 15) & ~15;
-  static constexpr int kFixedBytes = ((oSS + (int)sizeof(StackScalars)) + 15) & ~15;  // scratch vectors follow
+  // sticky launches: the chain's adaptation scalars and both step sizes stay here between its transitions (12 doubles)
+  static constexpr int oKeep = ((oSS + (int)sizeof(StackScalars)) + 15) & ~15;
+  static constexpr int kFixedBytes = ((oKeep + 12 * 8) + 15) & ~15;  // scratch vectors follow
 };
 
 // The warp's all-reduce through the shared-memory table instead of a shuffle butterfly: lane n stores value n of every
@@ -140,6 +142,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
   int* const vWe = reinterpret_cast<int*>(base + LY::oInts);  // [B]
   int* const lstk_i = vWe + B;                                // [kLog + 1][3] = we, ae, pidx
   StackScalars* const ss = reinterpret_cast<StackScalars*>(base + LY::oSS);
+  double* const keep = reinterpret_cast<double*>(base + LY::oKeep);  // [0..8] adaptation scalars, [10] exp(log_step), [11] exp(log_bar)
   Scratch<G, NP> sc;
   sc.sm = reinterpret_cast<double2*>(base + LY::kFixedBytes);
   sc.ws = reinterpret_cast<double2*>(reinterpret_cast<char*>(a.workspace) + sched_bytes(a.n_chains)) +
@@ -293,8 +296,11 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
         status |= LMC_STATUS_BAD_INITIAL_ENERGY;
         dead = true;
       } else {
-        double eps = exp_cold(__ldcg(a.adapt + (size_t)chain * LMC_ADAPT_STRIDE +
-                                     (adapt_step ? LMC_ADAPT_LOG_STEP : LMC_ADAPT_LOG_BAR)));
+        // a sticky chain's step sizes were formed by its previous epilogue (for the statistics row): no L2 round trip and
+        // no exp() at the head of the transition
+        double eps = (sticky && t > 0) ? keep[adapt_step ? 10 : 11]
+                                       : exp_cold(__ldcg(a.adapt + (size_t)chain * LMC_ADAPT_STRIDE +
+                                                         (adapt_step ? LMC_ADAPT_LOG_STEP : LMC_ADAPT_LOG_BAR)));
         if (a.step_size_override) eps = __ldg(a.step_size_override + chain);
         bool diverging = false, reached_max = false;
         const int max_depth = (tune && it < 200) ? a.early_max_treedepth : a.max_treedepth;  // nuts.py:205-208
@@ -760,10 +766,18 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
         for (int k = 0; k < NP; ++k) q[k] = sc.ld(tvid(tail, T_PROPQ), k);  // hmc_step.end.q
 
         double* const ad = a.adapt + (size_t)chain * LMC_ADAPT_STRIDE;
-        DualAvg da{__ldcg(ad + LMC_ADAPT_LOG_STEP), __ldcg(ad + LMC_ADAPT_LOG_BAR), __ldcg(ad + LMC_ADAPT_HBAR),
-                   __ldcg(ad + LMC_ADAPT_COUNT), __ldcg(ad + LMC_ADAPT_MU)};
-        WelfordScalars wel{__ldcg(ad + LMC_ADAPT_W_FG), __ldcg(ad + LMC_ADAPT_W_BG),
-                           (long long)__ldcg(ad + LMC_ADAPT_NSAMPLES), (long long)__ldcg(ad + LMC_ADAPT_WINDOW)};
+        const bool kept = sticky && t > 0;  // the scalars of a sticky chain are on chip since its previous transition
+        const double* const adr = kept ? keep : ad;
+        static_assert(LMC_ADAPT_LOG_STEP < 10 && LMC_ADAPT_WINDOW < 10, "keep[] mirrors the adapt row");
+        DualAvg da{kept ? adr[LMC_ADAPT_LOG_STEP] : __ldcg(ad + LMC_ADAPT_LOG_STEP),
+                   kept ? adr[LMC_ADAPT_LOG_BAR] : __ldcg(ad + LMC_ADAPT_LOG_BAR),
+                   kept ? adr[LMC_ADAPT_HBAR] : __ldcg(ad + LMC_ADAPT_HBAR),
+                   kept ? adr[LMC_ADAPT_COUNT] : __ldcg(ad + LMC_ADAPT_COUNT),
+                   kept ? adr[LMC_ADAPT_MU] : __ldcg(ad + LMC_ADAPT_MU)};
+        WelfordScalars wel{kept ? adr[LMC_ADAPT_W_FG] : __ldcg(ad + LMC_ADAPT_W_FG),
+                           kept ? adr[LMC_ADAPT_W_BG] : __ldcg(ad + LMC_ADAPT_W_BG),
+                           (long long)(kept ? adr[LMC_ADAPT_NSAMPLES] : __ldcg(ad + LMC_ADAPT_NSAMPLES)),
+                           (long long)(kept ? adr[LMC_ADAPT_WINDOW] : __ldcg(ad + LMC_ADAPT_WINDOW))};
         if (adapt_step) dual_average_update(da, accept_stat, a.target_accept, a.gamma, a.k, a.t0);
         if (tune && a.adapt_mass) {
           const size_t off = (size_t)chain * a.ld;
@@ -794,14 +808,28 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
           srow[LMC_STAT_MODEL_LOGP] = tr.prop_logp;
           srow[LMC_STAT_DIVERGING] = diverging ? 1.0 : 0.0;
           srow[LMC_STAT_TUNE] = tune ? 1.0 : 0.0;
-          srow[LMC_STAT_STEP_SIZE] = exp_cold(da.log_step);
-          srow[LMC_STAT_STEP_SIZE_BAR] = exp_cold(da.log_bar);
           srow[LMC_STAT_N_UNIFORMS] = (double)uc;
           srow[LMC_STAT_REACHED_MAX_TREEDEPTH] = reached_max ? 1.0 : 0.0;
         }
         store_row<G, NP>(a.q + (size_t)chain * a.ld, lane, ldh, q);
         __syncwarp();  // every lane has read the adaptation scalars before lane 0 overwrites them
         if (lane == 0) {
+          const double e_step = exp_cold(da.log_step), e_bar = exp_cold(da.log_bar);
+          srow[LMC_STAT_STEP_SIZE] = e_step;
+          srow[LMC_STAT_STEP_SIZE_BAR] = e_bar;
+          if (sticky) {
+            keep[LMC_ADAPT_LOG_STEP] = da.log_step;
+            keep[LMC_ADAPT_LOG_BAR] = da.log_bar;
+            keep[LMC_ADAPT_HBAR] = da.hbar;
+            keep[LMC_ADAPT_COUNT] = da.count;
+            keep[LMC_ADAPT_MU] = da.mu;
+            keep[LMC_ADAPT_W_FG] = wel.w_fg;
+            keep[LMC_ADAPT_W_BG] = wel.w_bg;
+            keep[LMC_ADAPT_NSAMPLES] = (double)wel.n_samples;
+            keep[LMC_ADAPT_WINDOW] = (double)wel.window;
+            keep[10] = e_step;
+            keep[11] = e_bar;
+          }
           ad[LMC_ADAPT_LOG_STEP] = da.log_step;
           ad[LMC_ADAPT_LOG_BAR] = da.log_bar;
           ad[LMC_ADAPT_HBAR] = da.hbar;
