@@ -48,7 +48,11 @@ struct WarpLayout {
   static constexpr int oRingP = 0;
   static constexpr int oPs = oRingP + B * VS * 16;
   static constexpr int oVar = oPs + (B / 2) * VS * 16;
-  static constexpr int oPart = oVar + VS * 16;
+  // sticky launches, NP <= 2: 1/sqrt(var) next to var, refreshed only when var changes (after tuning the momentum draw
+  // of a chain that stays on its warp needs no IEEE sqrt + divide per element); NP = 4 would lose a resident chain per SM
+  static constexpr bool kIstd = NP <= 2;
+  static constexpr int oIstd = oVar + VS * 16;
+  static constexpr int oPart = oIstd + (kIstd ? VS * 16 : 0);
   static constexpr int kRowLd = 34;                  // doubles per table row (32 + 2: conflict-free 128-bit row reads)
   static constexpr int oVal = oPart + kRows * kRowLd * 8;
   // val: E[B], logp[B], dE[B], wm[B], pre[2B], dot[4B-6 (+pad)], local stack (kLog + 1) x 5 doubles, we[B] ints, lpidx ints
@@ -131,6 +135,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
   double2* const ring_p = reinterpret_cast<double2*>(base + LY::oRingP) + lane;  // [B][NP][32]
   double2* const psbuf = reinterpret_cast<double2*>(base + LY::oPs) + lane;     // [B/2][NP][32]
   double2* const s_var = reinterpret_cast<double2*>(base + LY::oVar) + lane;    // [NP][32]
+  double2* const s_istd = reinterpret_cast<double2*>(base + LY::oIstd) + lane;  // [NP][32] (kIstd)
   double* const part = reinterpret_cast<double*>(base + LY::oPart);             // [kRows][34]: row = value, column = lane
   double* const vE = reinterpret_cast<double*>(base + LY::oVal);
   double* const vLogp = vE + B;
@@ -268,9 +273,23 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
           } else if (2 * j < D) {
             n = philox_normal_pair(seed, it, (uint32_t)j);
           }
-          const double2 vk = s_var[k * 32];
-          p[k].x = (2 * j < D) ? mul_rn(inv_sqrt_cold(vk.x), n.x) : 0.0;
-          p[k].y = (2 * j + 1 < D) ? mul_rn(inv_sqrt_cold(vk.y), n.y) : 0.0;
+          double2 is;
+          if constexpr (LY::kIstd) {
+            // var changed since this warp last formed 1/sqrt(var)?  (first transition of the launch, a chain popped from
+            // the FIFO, or the previous transition updated the mass matrix)
+            if (!sticky || t == 0 || (it - 1 < a.n_tune && a.adapt_mass)) {
+              const double2 vk = s_var[k * 32];
+              is = make_double2(inv_sqrt_cold(vk.x), inv_sqrt_cold(vk.y));
+              s_istd[k * 32] = is;
+            } else {
+              is = s_istd[k * 32];
+            }
+          } else {
+            const double2 vk = s_var[k * 32];
+            is = make_double2(inv_sqrt_cold(vk.x), inv_sqrt_cold(vk.y));
+          }
+          p[k].x = (2 * j < D) ? mul_rn(is.x, n.x) : 0.0;
+          p[k].y = (2 * j + 1 < D) ? mul_rn(is.y, n.y) : 0.0;
         }
       }
 
@@ -814,7 +833,9 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
         store_row<G, NP>(a.q + (size_t)chain * a.ld, lane, ldh, q);
         __syncwarp();  // every lane has read the adaptation scalars before lane 0 overwrites them
         if (lane == 0) {
-          const double e_step = exp_cold(da.log_step), e_bar = exp_cold(da.log_bar);
+          // (after tuning the step sizes do not move: a sticky chain reuses the pair it formed last time)
+          const bool same = kept && !adapt_step;
+          const double e_step = same ? keep[10] : exp_cold(da.log_step), e_bar = same ? keep[11] : exp_cold(da.log_bar);
           srow[LMC_STAT_STEP_SIZE] = e_step;
           srow[LMC_STAT_STEP_SIZE_BAR] = e_bar;
           if (sticky) {
