@@ -106,9 +106,6 @@ struct TableGroup {
 #ifndef LMC_WARP_LANE_TREE
 #define LMC_WARP_LANE_TREE 1
 #endif
-#ifndef LMC_WARP_POPAHEAD
-#define LMC_WARP_POPAHEAD 0
-#endif
 // LMC_WARP_TIMING: lane 0 of every CTA's first warp accumulates clock64() deltas per phase (index = the phase that just
 // ENDED) and block 0 prints its totals -- a development probe (-DLMC_WARP_TIMING=1 variant build, tools/quick_bench.py)
 #ifdef LMC_WARP_TIMING
@@ -203,14 +200,6 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
   int t_next = 0;
   bool sticky_dead = false;
   double2 q[NP];
-#if LMC_WARP_POPAHEAD
-  // FIFO launches, lane 0: the pop of the NEXT unit is issued early and consumed late (lmc_sampler.cuh: ticket / peek /
-  // take) -- the ticket when the epilogue starts, the ring entry when it ends -- so that of the pop's two dependent L2 round
-  // trips nothing is left between two transitions when the queue is not empty.
-  unsigned nx_ticket = 0u;
-  unsigned long long nx_entry = 0ull;
-  bool nx_have = false;
-#endif
 
   for (;;) {
     // ---- the next (chain, transition) unit: own chain (sticky) or popped from the FIFO (lmc_sampler.cuh: scheduler) ----
@@ -221,18 +210,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
         t = t_next++;
       }
     } else {
-#if LMC_WARP_POPAHEAD
-      if (lane == 0) {
-        if (!nx_have) {  // first unit of this warp, or the previous one was a dead chain's (no epilogue)
-          nx_ticket = sched_ticket(sv);
-          nx_entry = sched_peek(sv, nx_ticket, total_units, (unsigned)a.n_chains);
-        }
-        sched_take(sv, nx_ticket, nx_entry, total_units, (unsigned)a.n_chains, chain, t);
-        nx_have = false;
-      }
-#else
       if (lane == 0) sched_pop(sv, total_units, (unsigned)a.n_chains, chain, t);
-#endif
       chain = __shfl_sync(FULL, chain, 0);
       t = __shfl_sync(FULL, t, 0);
     }
@@ -802,12 +780,6 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
           }
         }
         LMC_WTICK(10);
-#if LMC_WARP_POPAHEAD
-        if (!sticky && lane == 0) {
-          nx_ticket = sched_ticket(sv);  // in flight while the epilogue runs
-          nx_have = true;
-        }
-#endif
         const double accept_stat = mean_tree_accept(tr);
 #pragma unroll
         for (int k = 0; k < NP; ++k) q[k] = sc.ld(tvid(tail, T_PROPQ), k);  // hmc_step.end.q
@@ -888,9 +860,6 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
           ad[LMC_ADAPT_NSAMPLES] = (double)wel.n_samples;
           ad[LMC_ADAPT_WINDOW] = (double)wel.window;
         }
-#if LMC_WARP_POPAHEAD
-        if (!sticky && lane == 0) nx_entry = sched_peek(sv, nx_ticket, total_units, (unsigned)a.n_chains);
-#endif
       }
       if (lane == 0 && status) atomicOr(a.status + chain, status);
     }

@@ -22,6 +22,10 @@ target = arg[7] if len(arg) > 7 else "gauss"
 depth = int(arg[8]) if len(arg) > 8 else 10
 warm = int(arg[9]) if len(arg) > 9 else 100
 early = int(arg[10]) if len(arg) > 10 else 8   # early_max_treedepth (the cap while iteration < 200)
+# QB_EPS=<step size>: every chain integrates with this fixed step size in the timed launch (step_size_override); a tiny
+# one makes every tree reach max_treedepth without a U-turn -- the single-chain latency probe for deep trees
+import os  # noqa: E402
+fixed_eps = float(os.environ["QB_EPS"]) if os.environ.get("QB_EPS") else None
 
 dev = "cuda:0"
 if target == "funnel":
@@ -48,8 +52,9 @@ for g in groups:
                     torch.cuda.synchronize()
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
+                    ov = None if fixed_eps is None else torch.full((C,), fixed_eps, dtype=torch.float64, device=dev)
                     tr, st = engine.run_transitions(L.KIND_NUTS, ch, tgt, n_trans=T, iter0=warm, n_tune=10**9,
-                                                    params=params, seeds=seeds, knobs=knobs)
+                                                    params=params, seeds=seeds, knobs=knobs, step_size_override=ov)
                     e1.record()
                     torch.cuda.synchronize()
                 except Exception as e:  # unsupported shape
