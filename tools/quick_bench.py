@@ -33,8 +33,11 @@ if target == "funnel":
 else:
     sigma = 10 ** np.linspace(-0.5, 0.5, D)
     tgt = engine.FusedTarget(L.TARGET_DIAG_GAUSSIAN, D, tau=1 / sigma**2)
+# QB_ADAPT_MASS / QB_ADAPT_STEP = 0 switch one adaptation off in the TIMED launch; QB_TUNE = its n_tune (0: tuning is over)
 params = dict(adapt_mass=1, adapt_step_size=1, target_accept=0.8, gamma=0.05, k=0.75, t0=10, Emax=1000.0,
               max_treedepth=depth, early_max_treedepth=early)
+params_timed = dict(params, adapt_mass=int(os.environ.get("QB_ADAPT_MASS", "1")),
+                    adapt_step_size=int(os.environ.get("QB_ADAPT_STEP", "1")))
 seeds = engine.seeds_tensor(np.arange(C) + 12345, dev)
 for g in groups:
     for sm in smems:
@@ -53,8 +56,9 @@ for g in groups:
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
                     ov = None if fixed_eps is None else torch.full((C,), fixed_eps, dtype=torch.float64, device=dev)
-                    tr, st = engine.run_transitions(L.KIND_NUTS, ch, tgt, n_trans=T, iter0=warm, n_tune=10**9,
-                                                    params=params, seeds=seeds, knobs=knobs, step_size_override=ov)
+                    tr, st = engine.run_transitions(L.KIND_NUTS, ch, tgt, n_trans=T, iter0=warm,
+                                                    n_tune=int(os.environ.get("QB_TUNE", 10**9)),
+                                                    params=params_timed, seeds=seeds, knobs=knobs, step_size_override=ov)
                     e1.record()
                     torch.cuda.synchronize()
                 except Exception as e:  # unsupported shape
