@@ -253,7 +253,7 @@ def make_target(lmc, kind, D, dev, logp):
     tparams = target_params(kind, D)
     if logp == "user-source":     # the density as user CUDA source, compiled into the fused kernel at run time (NVRTC)
         assert kind in ("gauss", "illcond")
-        return lmc.targets.ElementwiseTarget(D, logp="0.5 * q * (-(tau * q))", grad="-(tau * q)",
+        return lmc.targets.ElementwiseTarget(D, logp="0.5 * q * g", grad="-(tau * q)",
                                              params={"tau": tparams["tau"]})
     target = (lmc.targets.NealFunnel(D) if kind == "funnel" else lmc.targets.DiagGaussian(tau=tparams["tau"]))
     if logp != "fused":           # the density as a batched torch op around the state-machine kernel (callback mode)
@@ -505,6 +505,14 @@ def run_gpu_arm(args):
                     r.pop(k)
                 r["workload"] = "%s: %s" % (wl, WORKLOADS[wl][6])
                 if wl == "cfg4":
+                    # steps whose transitions all run under the early depth cap (iteration < 200) vs the rest
+                    tps_ = r["transitions_per_step"]
+                    capped = [k for k in range(n_steps) if (3 + k + 1) * tps_ <= 200]
+                    rest = [k for k in range(n_steps) if k not in capped]
+                    for name_, ks in (("value_steps_under_early_depth_cap", capped), ("value_steps_after_cap_lifts", rest)):
+                        if ks:
+                            r[name_] = (sum(r["leapfrogs_per_step_each"][k] for k in ks) /
+                                        (sum(r["ms_per_step_each"][k] for k in ks) * 1e-3))
                     r["note"] = ("a launch lasts as long as its slowest chain: once the early depth cap (8, while tuning and "
                                  "iter_count < 200) lifts, the few chains sitting in the funnel's neck with a tiny adapted "
                                  "step size build depth-12 trees (4095 leapfrogs) transition after transition, strictly "

@@ -68,8 +68,14 @@ __global__ void cb_begin_kernel(const lmc_callback_args c, size_t vec_off) {
   (void)vec_off;
 }
 
+// Registers are capped at 128 per thread (512 resident threads per SM-quarter's worth of registers): the kernel is a
+// chain of dependent L2 round trips per CTA, so what counts is how many chains are resident at once -- 1024 chains of
+// 64 threads fit in ONE wave at 8 CTAs per SM (145 registers gave 6: a second wave of 136 CTAs doubled the launch)
+template <int G>
+__host__ __device__ constexpr int cb_min_blocks() { return cb_block<G>() >= 512 ? 1 : 512 / cb_block<G>(); }
+
 template <int G, int NP, int KIND>
-__global__ void __launch_bounds__(cb_block<G>()) cb_advance_kernel(const lmc_callback_args c, size_t vec_off, int n_vecs) {
+__global__ void __launch_bounds__(cb_block<G>(), cb_min_blocks<G>()) cb_advance_kernel(const lmc_callback_args c, size_t vec_off, int n_vecs) {
   constexpr int CPB = cb_block<G>() / G;
   constexpr int VS = G * NP;
   const lmc_sampler_args& a = c.base;

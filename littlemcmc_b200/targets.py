@@ -32,12 +32,14 @@ class DiagGaussian:
         """The same density as a batched torch op (callback mode instead of the fused kernel)."""
         import torch
         neg_tau = torch.as_tensor(-self.tau, dtype=torch.float64, device=device)
-        half_neg_tau = 0.5 * neg_tau
+
+        zero = torch.zeros(1, 1, 1, dtype=torch.float64, device=device)
 
         def fn(q):
-            # three kernels per evaluation (callback mode is bound by launches per gradient, not by bytes):
-            # g = q * (-tau) [bitwise -(tau * q)], logp = (q * q) @ (-tau / 2)
-            return torch.mv(q * q, half_neg_tau), q * neg_tau
+            # two kernels per evaluation (callback mode is bound by launches per gradient, not by bytes):
+            # g = q * (-tau) [bitwise -(tau * q)]; logp = 0.5 * <q, g> per chain as ONE strided-batched GEMM (alpha = 0.5)
+            g = q * neg_tau
+            return torch.baddbmm(zero, q.unsqueeze(1), g.unsqueeze(2), beta=0, alpha=0.5).view(-1), g
         return TorchBatched(fn, cuda_graph=cuda_graph)
 
 
@@ -74,15 +76,23 @@ class NealFunnel:
         import torch
         inv_s2, half_nm1 = 1.0 / (self.v_scale * self.v_scale), 0.5 * (self.ndim - 1)
 
+        def c(x):
+            return torch.full((1, 1), float(x), dtype=torch.float64, device=device)
+        zero, zero3, c_h, c_nh = c(0.0), torch.zeros(1, 1, 1, dtype=torch.float64, device=device), c(half_nm1), c(-half_nm1)
+
         def fn(q):
-            v, x = q[:, 0], q[:, 1:]
-            S = (x * x).sum(1)
-            ev = torch.exp(-v)
-            hs = 0.5 * ev * S
-            g = torch.empty_like(q)
-            g[:, 1:] = -(ev[:, None] * x)
-            g[:, 0] = -(v * inv_s2) + hs - half_nm1
-            return -(0.5 * v * v * inv_s2) - hs - half_nm1 * v, g
+            # ten small kernels per evaluation instead of the ~20 of the literal transcription: every line is ONE kernel
+            # (addcmul / add-with-alpha fold the constants; the scalar-per-chain quantities are [C, 1] columns)
+            v, x = q[:, :1], q[:, 1:]
+            ev = torch.exp(-v)                                                        # (2 kernels) e^-v
+            g = torch.addcmul(zero, q, ev, value=-1.0)                                # -(ev * q): columns 1.. are final
+            S = torch.baddbmm(zero3, x.unsqueeze(1), x.unsqueeze(2), beta=0).view(-1, 1)   # sum_i x_i^2
+            nhs = torch.addcmul(zero, ev, S, value=-0.5)                              # -hs = -(ev * S) / 2
+            r = torch.add(c_h, v, alpha=0.5 * inv_s2)                                 # v / (2 s^2) + (n-1)/2
+            logp = torch.addcmul(nhs, v, r, value=-1.0)                               # -hs - v^2 / (2 s^2) - (n-1)/2 v
+            s1 = torch.add(nhs, v, alpha=inv_s2)                                      # -hs + v / s^2
+            torch.sub(c_nh, s1, out=g[:, :1])                                         # g_0 = hs - v / s^2 - (n-1)/2
+            return logp.view(-1), g
         return TorchBatched(fn, cuda_graph=cuda_graph)
 
 
@@ -121,23 +131,27 @@ struct %(name)s {
 #pragma unroll
     for (int k = 0; k < NP; ++k) {
       const int j = lane + k * G;
-      double2 gk = make_double2(0.0, 0.0);
-      if (j < ldh) {
+      // parameter loads as selects and NO branch around the element code (like the built-in targets): the compiler hoists
+      // the read-only loads out of the leapfrog loop; an element beyond ndim is evaluated at q = 0 with zero parameters and
+      // its results are discarded by selects (whatever they are, NaN included)
 %(loads)s
-        // both elements are evaluated unconditionally (selects, no branches); an element beyond ndim contributes nothing
-        const bool in_x = 2 * j < D, in_y = 2 * j + 1 < D;
-        {
-          const double q = q_[k].x;
+      const bool in_x = 2 * j < D, in_y = 2 * j + 1 < D;
+      double2 gk;
+      {  // the gradient of an element is in scope of its `logp` expression as `g`
+        const double q = q_[k].x;
 %(bind_x)s
-          gk.x = in_x ? (%(grad)s) : 0.0;
-          part += in_x ? (%(logp)s) : 0.0;
-        }
-        {
-          const double q = q_[k].y;
+        const double g = (%(grad)s);
+        const double l = (%(logp)s);
+        gk.x = in_x ? g : 0.0;
+        part += in_x ? l : 0.0;
+      }
+      {
+        const double q = q_[k].y;
 %(bind_y)s
-          gk.y = in_y ? (%(grad)s) : 0.0;
-          part += in_y ? (%(logp)s) : 0.0;
-        }
+        const double g = (%(grad)s);
+        const double l = (%(logp)s);
+        gk.y = in_y ? g : 0.0;
+        part += in_y ? l : 0.0;
       }
       g_[k] = gk;
     }
@@ -150,30 +164,34 @@ struct %(name)s {
 
 class ElementwiseTarget(CudaTarget):
     """Separable density ``logp(q) = sum_i f(q_i; theta_i)`` from two C expressions: ``logp`` = f and ``grad`` = df/dq,
-    written in terms of ``q`` and the names of ``params`` (a dict name -> array[ndim] or scalar).  Example (the built-in
-    diagonal Gaussian): ``ElementwiseTarget(D, logp="0.5 * q * (-(tau * q))", grad="-(tau * q)", params={"tau": tau})``.
+    written in terms of ``q`` and the names of ``params`` (a dict name -> array[ndim] or scalar); ``logp`` may also use
+    ``g``, the value of the ``grad`` expression at that element (``g`` is therefore not available as a parameter name).
+    Example (the built-in diagonal Gaussian): ``ElementwiseTarget(D, logp="0.5 * q * g", grad="-(tau * q)",
+    params={"tau": tau})``.
     The same expressions are evaluated with NumPy for the reference-style callable (exp, log, sqrt, tanh ... map to
     numpy's).  Multiply-adds are not contracted (-fmad=false), as in NumPy."""
 
     def __init__(self, ndim, logp, grad, params=None):
         import hashlib
         params = {k: np.broadcast_to(np.asarray(v, dtype="d"), (int(ndim),)).copy() for k, v in (params or {}).items()}
+        if "g" in params or "q" in params:
+            raise ValueError("`q` and `g` are the element and its gradient inside the expressions, not parameter names")
         names = sorted(params)
         ld = int(ndim) + (int(ndim) & 1)
         blob = np.zeros((max(1, len(names)), ld))
         for i, n in enumerate(names):
             blob[i, :ndim] = params[n]
         name = "LmcElementwise_" + hashlib.sha256(repr((logp, grad, names)).encode()).hexdigest()[:12]
-        loads = "\n".join("        const double2 %s_2 = __ldg(reinterpret_cast<const double2*>(params + %d * 2 * (size_t)ldh) + j);"
-                          % (n, i) for i, n in enumerate(names))
+        loads = "\n".join("      const double2 %s_2 = j < ldh ? __ldg(reinterpret_cast<const double2*>(params + %d * 2 * (size_t)ldh) + j)"
+                          " : make_double2(0.0, 0.0);" % (n, i) for i, n in enumerate(names))
         bind = lambda c: "\n".join("          const double %s = %s_2.%s;" % (n, n, c) for n in names)  # noqa: E731
         src = _ELEMENTWISE_TEMPLATE % dict(name=name, loads=loads, bind_x=bind("x"), bind_y=bind("y"), grad=grad, logp=logp)
         env = {k: getattr(np, k) for k in ("exp", "log", "sqrt", "tanh", "sin", "cos", "log1p", "expm1", "fabs")}
 
         def numpy_fn(q):
             scope = dict(env, q=np.asarray(q, dtype="d"), **params)
-            return float(np.sum(eval(logp, {"__builtins__": {}}, scope))), np.asarray(eval(grad, {"__builtins__": {}}, scope),
-                                                                                       dtype="d") * np.ones(int(ndim))
+            gval = np.asarray(eval(grad, {"__builtins__": {}}, scope), dtype="d") * np.ones(int(ndim))
+            return float(np.sum(eval(logp, {"__builtins__": {}}, dict(scope, g=gval)))), gval
         super().__init__(src, name, ndim, params=blob, numpy_fn=numpy_fn)
         self.logp_expr, self.grad_expr, self.params = logp, grad, params
 

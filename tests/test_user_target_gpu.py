@@ -54,10 +54,23 @@ struct UserFunnel {
 """
 
 
-def _user_gauss(case):
+def _user_gauss(case, logp="0.5 * q * (-(tau * q))"):
     import littlemcmc_b200 as lmc
-    return lmc.targets.ElementwiseTarget(int(case["ndim"]), logp="0.5 * q * (-(tau * q))", grad="-(tau * q)",
+    return lmc.targets.ElementwiseTarget(int(case["ndim"]), logp=logp, grad="-(tau * q)",
                                          params={"tau": np.asarray(case["tau"], dtype="d")})
+
+
+@pytest.mark.parametrize("name", ["nuts_diag_d37", "nuts_static_d100"])
+def test_user_gaussian_logp_in_terms_of_the_gradient(name):
+    """`g` inside the `logp` expression is the element's gradient; D = 37 exercises the half-filled last pair."""
+    case, _ = gc.load(name)
+    tgt = _user_gauss(case, logp="0.5 * q * g")
+    q = np.linspace(-1, 1, int(case["ndim"]))
+    lp, g = tgt(q)
+    lp0, g0 = gc.target_fn(case)()(q)
+    assert np.array_equal(g, g0) and abs(lp - lp0) <= 1e-12 * abs(lp0)
+    res = pu.run_case_on_gpu_and_oracle(name, target=tgt.fused)
+    pu.assert_parity(res, rtol=RTOL)
 
 
 @pytest.mark.parametrize("name", ["nuts_b1_d10", "nuts_diag_d37", "nuts_static_d100", "nuts_deep_d100",
