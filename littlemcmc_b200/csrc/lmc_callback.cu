@@ -85,6 +85,16 @@ __global__ void __launch_bounds__(cb_block<G>(), cb_min_blocks<G>()) cb_advance_
   const int chain = blockIdx.x * CPB + gib;
   if (chain >= a.n_chains) return;  // G == 32: per-warp exit; G >= 64: CPB == 1, whole block exits together
   CbMachine* const M = reinterpret_cast<CbMachine*>(reinterpret_cast<char*>(c.machine) + (size_t)chain * kMachineBytes);
+  // the rows every phase needs are requested BEFORE the machine state is looked at: one L2 round trip instead of two on
+  // the critical path of a launch that is nothing but dependent round trips (a finished chain wastes three loads)
+  const int D = a.ndim;
+  const int ldh = (int)(a.ld >> 1);
+  const size_t off = (size_t)chain * a.ld;
+  double2 q[NP], p[NP], g[NP], var[NP];
+  load_row<G, NP>(c.q_eval + off, lane, ldh, q);
+  load_row<G, NP>(c.g_eval + off, lane, ldh, g);
+  load_row<G, NP>(a.var + off, lane, ldh, var);
+  const double logp = c.logp_eval[chain];
   CbScalars s = M->s;
   if (s.phase == PH_DONE) return;
   Group<G> grp(lane, red_s + gib * (2 * Group<G>::kWarps * kRedSlots));
@@ -98,17 +108,9 @@ __global__ void __launch_bounds__(cb_block<G>(), cb_min_blocks<G>()) cb_advance_
   const int V_Q0 = 1;                                                     // HMC: the transition's start position
   const int tail = vid_tail(scratch_depth(a));
 
-  const int D = a.ndim;
-  const int ldh = (int)(a.ld >> 1);
-  const size_t off = (size_t)chain * a.ld;
-  double2 q[NP], p[NP], g[NP], var[NP];
-  load_row<G, NP>(c.q_eval + off, lane, ldh, q);
-  load_row<G, NP>(c.g_eval + off, lane, ldh, g);
-  load_row<G, NP>(a.var + off, lane, ldh, var);
   mask_tail<G, NP>(lane, D, q);
   mask_tail<G, NP>(lane, D, g);
   mask_tail<G, NP>(lane, D, var);
-  const double logp = c.logp_eval[chain];
 
   double* const ad = a.adapt + (size_t)chain * LMC_ADAPT_STRIDE;
   const long long it = a.iter0 + s.t;  // BaseHMC.iter_count

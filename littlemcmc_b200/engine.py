@@ -388,7 +388,7 @@ class CallbackRun:
         with torch.cuda.device(dev):
             self.begin()
             if cuda_graph in (True, "device"):
-                self._run_device_loop(iters_per_graph or 4)
+                self._run_device_loop(iters_per_graph or 8)
             elif cuda_graph == "replay":
                 self._run_graphed(iters_per_graph or 8)
             elif cuda_graph:
@@ -538,7 +538,7 @@ def run_transitions_callback(kind, chains, callback, *, n_trans, iter0, n_tune, 
                 for r in runs:
                     r.begin()
                 n_running.fill_(Cn)          # every begin wrote its own batch size: the shared counter is their sum
-                _device_loop(runs, 4)
+                _device_loop(runs, 8)
             return trace, stats
     run = CallbackRun(kind, chains, callback, n_trans=n_trans, iter0=iter0, n_tune=n_tune, params=params, seeds=seeds,
                       tapes=tapes, trace=trace, stats=stats, step_size_override=step_size_override)
