@@ -262,6 +262,58 @@ struct DiagGaussian {
   __device__ __forceinline__ double finish(double sum, const double (&)[2]) const { return 0.5 * sum; }
 };
 
+// DiagGaussian with tau read from a zero-padded copy in shared memory ([NP][32] pairs, pointer already offset by the
+// lane): what the chunked warp kernel evaluates when a resident chain's shared memory has room for it (StageTraits)
+struct DiagGaussianStaged {
+  static constexpr int kPre = 0;
+  const double2* tau_s;
+
+  template <int G, int NP>
+  __device__ __forceinline__ void pre(int, int, const double2 (&)[NP], double (&)[2]) const {}
+
+  template <int G, int NP>
+  __device__ __forceinline__ double grad(int, int, int, const double2 (&q)[NP], double2 (&g)[NP], const double (&)[2]) const {
+    double part = 0.0;
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      const double2 t = tau_s[k * G];
+      g[k] = make_double2(-mul_rn(t.x, q[k].x), -mul_rn(t.y, q[k].y));  // as DiagGaussian::grad
+      part = dot2(part, q[k], g[k]);
+    }
+    return part;
+  }
+  __device__ __forceinline__ double finish(double sum, const double (&)[2]) const { return 0.5 * sum; }
+};
+
+template <bool C, class A, class B>
+struct Cond { using type = A; };
+template <class A, class B>
+struct Cond<false, A, B> { using type = B; };
+
+// Per-dimension parameter vectors of a target that a kernel may stage in shared memory once per launch: kVecs of them,
+// `make` fills the copy (every lane its own NP pairs) and returns the target that reads it.  Default: nothing staged.
+template <class T>
+struct StageTraits {
+  static constexpr int kVecs = 0;
+  using Staged = T;
+  template <int NP>
+  static __device__ __forceinline__ Staged make(const T& t, double2*, int, int) { return t; }
+};
+template <>
+struct StageTraits<DiagGaussian> {
+  static constexpr int kVecs = 1;
+  using Staged = DiagGaussianStaged;
+  template <int NP>
+  static __device__ __forceinline__ Staged make(const DiagGaussian& t, double2* s_lane, int lane, int ldh) {
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      const int j = lane + k * 32;
+      s_lane[k * 32] = (j < ldh) ? __ldg(t.tau + j) : make_double2(0.0, 0.0);
+    }
+    return DiagGaussianStaged{s_lane};
+  }
+};
+
 struct Funnel {
   static constexpr int kPre = 2;  // [0] = S = sum_{i>=1} q_i^2, [1] = v = q_0 (only its owner contributes)
   double inv_s2;                  // 1 / v_scale^2

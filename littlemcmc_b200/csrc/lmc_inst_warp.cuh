@@ -5,7 +5,9 @@
 namespace lmc {
 
 // (NP, B, min resident CTAs per SM -> register cap 65536 / (32 * MINB))
-#define LMC_WARP_SHAPES(X) X(1, 4, 16) X(1, 8, 16) X(1, 16, 12) X(2, 4, 12) X(2, 8, 12) X(2, 16, 8) X(4, 4, 8) X(4, 8, 8)
+// (the cap follows what shared memory lets be resident anyway: 10 chains per SM at (1, 8), 7 at (2, 8) -- with 128 / 168
+// registers ptxas rematerialised and re-loaded; at 168 / 216: cfg4's bulk +6%, cfg2 +1%, a chain alone +3%)
+#define LMC_WARP_SHAPES(X) X(1, 4, 16) X(1, 8, 10) X(1, 16, 12) X(2, 4, 12) X(2, 8, 7) X(2, 16, 8) X(4, 4, 8) X(4, 8, 8)
 
 // default chunk: as long as the memory of a resident chain allows a useful number of chains per SM
 inline int default_chunk(int np) { return np >= 4 ? 4 : 8; }

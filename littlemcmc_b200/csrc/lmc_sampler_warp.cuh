@@ -62,8 +62,15 @@ struct WarpLayout {
   static constexpr int oSS = ((oInts + nInts * 4) + 15) & ~15;
   // sticky launches: the chain's adaptation scalars and both step sizes stay here between its transitions (12 doubles)
   static constexpr int oKeep = ((oSS + (int)sizeof(StackScalars)) + 15) & ~15;
-  static constexpr int kFixedBytes = ((oKeep + 12 * 8) + 15) & ~15;  // scratch vectors follow
+  static constexpr int kFixedBytes = ((oKeep + 12 * 8) + 15) & ~15;  // (staged target parameters,) scratch vectors follow
+  // a target's per-dimension parameters (StageTraits) are staged after the fixed part where that costs no resident chain:
+  // NP = 2 (7 chains per SM with or without the extra KB); NP = 1 would drop from 10 to 9 chains per SM
+  static constexpr bool kStageOk = NP == 2;
 };
+template <class Target, int NP, int B>
+__host__ __device__ constexpr int warp_stage_vecs() {
+  return WarpLayout<NP, B>::kStageOk ? StageTraits<Target>::kVecs : 0;
+}
 
 // The warp's all-reduce through the shared-memory table instead of a shuffle butterfly: lane n stores value n of every
 // lane into row n, lane r sums row r, everybody reads the N totals back.  Same latency as the butterfly (two warp
@@ -121,7 +128,7 @@ struct TableGroup {
 #endif
 
 template <class Target, int NP, int B, int WPB, int MINB, bool TAPE>
-__global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_sampler_args a, const Target tgt,
+__global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_sampler_args a, const Target tgt_in,
                                                                       const WarpCfg cfg) {
   using LY = WarpLayout<NP, B>;
   constexpr int G = 32;
@@ -148,8 +155,9 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
   int* const lstk_i = vWe + B;                                // [kLog + 1][3] = we, ae, pidx
   StackScalars* const ss = reinterpret_cast<StackScalars*>(base + LY::oSS);
   double* const keep = reinterpret_cast<double*>(base + LY::oKeep);  // [0..8] adaptation scalars, [10] exp(log_step), [11] exp(log_bar)
+  constexpr int kStage = warp_stage_vecs<Target, NP, B>();
   Scratch<G, NP> sc;
-  sc.sm = reinterpret_cast<double2*>(base + LY::kFixedBytes);
+  sc.sm = reinterpret_cast<double2*>(base + LY::kFixedBytes + kStage * VS * 16);
   sc.ws = reinterpret_cast<double2*>(reinterpret_cast<char*>(a.workspace) + sched_bytes(a.n_chains)) +
           (size_t)slot * cfg.ws_vecs * VS;
   sc.n_smem = cfg.n_smem_vecs;
@@ -165,6 +173,19 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
 
   const int D = a.ndim;
   const int ldh = (int)(a.ld >> 1);
+  // the target as this warp evaluates it: its per-dimension parameters copied to shared memory once per launch where the
+  // slot has room (an L1-missing read-only load at the head of every doubling otherwise), else the caller's object
+  using EvalTarget = typename Cond<(kStage > 0), typename StageTraits<Target>::Staged, Target>::type;
+  const EvalTarget tgt = [&]() -> EvalTarget {
+    if constexpr (kStage > 0) {
+      const EvalTarget e = StageTraits<Target>::template make<NP>(
+          tgt_in, reinterpret_cast<double2*>(base + LY::kFixedBytes) + lane, lane, ldh);
+      __syncwarp();
+      return e;
+    } else {
+      return tgt_in;
+    }
+  }();
   const int sdepth = scratch_depth(a);
   const int tail = vid_tail(sdepth);
   // position ring of the current chunk: B vectors after the tree scratch of this slot (global, written once per leaf,
@@ -200,6 +221,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
   int t_next = 0;
   bool sticky_dead = false;
   double2 q[NP];
+  uint64_t seed_keep = 0ull;  // sticky launches: the chain's seed is read once, not once per transition
 
   for (;;) {
     // ---- the next (chain, transition) unit: own chain (sticky) or popped from the FIFO (lmc_sampler.cuh: scheduler) ----
@@ -237,7 +259,8 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
 #pragma unroll
         for (int k = 0; k < NP; ++k) s_var[k * 32] = var[k];
       }
-      const uint64_t seed = TAPE ? 0ull : a.rng.seeds[chain];
+      if (!TAPE && (!sticky || t == 0)) seed_keep = a.rng.seeds[chain];
+      const uint64_t seed = TAPE ? 0ull : seed_keep;
       const long long it = a.iter0 + t;
       const bool tune = it < a.n_tune;
       const bool adapt_step = tune && a.adapt_step_size;
@@ -900,7 +923,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) sampler_warp_kernel(const lmc_
 // `kern`: a sampler_warp_kernel instantiation of this library or a cudaKernel_t compiled at run time for a user target
 // (lmc_user.cu); `tgt`: host pointer to the kernel's by-value target argument.
 template <int NP, int B, int WPB>
-int launch_warp_kernel(const void* kern, const lmc_sampler_args& a, const void* tgt) {
+int launch_warp_kernel(const void* kern, const lmc_sampler_args& a, const void* tgt, int stage_vecs = 0) {
   using LY = WarpLayout<NP, B>;
   constexpr int VS = LY::VS;
   int dev = 0, n_sm = 0, smem_optin = 0;
@@ -915,7 +938,7 @@ int launch_warp_kernel(const void* kern, const lmc_sampler_args& a, const void* 
   const int hot = vid_tail(sdepth);
   if (n_smem > hot) n_smem = hot;
   cfg.n_smem_vecs = n_smem;
-  cfg.slot_bytes = LY::kFixedBytes + n_smem * VS * 16;
+  cfg.slot_bytes = LY::kFixedBytes + (stage_vecs + n_smem) * VS * 16;
   const size_t smem = (size_t)WPB * cfg.slot_bytes;
   if (smem > (size_t)smem_optin) return LMC_ERR_UNSUPPORTED;
   LMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -940,7 +963,7 @@ int launch_warp_kernel(const void* kern, const lmc_sampler_args& a, const void* 
 template <class Target, int NP, int B, int WPB, int MINB, bool TAPE>
 int launch_warp_mode(const lmc_sampler_args& a, const Target& tgt) {
   return launch_warp_kernel<NP, B, WPB>(reinterpret_cast<const void*>(sampler_warp_kernel<Target, NP, B, WPB, MINB, TAPE>),
-                                        a, &tgt);
+                                        a, &tgt, warp_stage_vecs<Target, NP, B>());
 }
 
 template <class Target, int NP, int B, int WPB, int MINB>
