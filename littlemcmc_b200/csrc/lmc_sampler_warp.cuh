@@ -71,6 +71,10 @@ template <class Target, int NP, int B>
 __host__ __device__ constexpr int warp_stage_vecs() {
   return WarpLayout<NP, B>::kStageOk ? StageTraits<Target>::kVecs : 0;
 }
+// the same number as a device variable: how the host learns it for a kernel compiled at run time around a user target
+// (lmc_user.cu reads it from the loaded module; the slot size of the launch must match what the kernel was built with)
+template <class Target, int NP, int B>
+__device__ const int warp_stage_probe = warp_stage_vecs<Target, NP, B>();
 
 // The warp's all-reduce through the shared-memory table instead of a shuffle butterfly: lane n stores value n of every
 // lane into row n, lane r sums row r, everybody reads the N totals back.  Same latency as the butterfly (two warp

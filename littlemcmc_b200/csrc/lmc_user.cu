@@ -80,6 +80,7 @@ struct lmc_user_kernel {
   cudaKernel_t kern;
   int warp;      // 1: sampler_warp_kernel<T, NP, B, 1, MINB, TAPE>; 0: sampler_kernel<T, G, NP, KIND>
   int kind, tape, NP, B, G;
+  int stage_vecs;  // warp kernel: parameter vectors the kernel stages in shared memory (warp_stage_probe of the module)
 };
 
 extern "C" const char* lmc_user_kernel_log(void) { return lmc::g_user_log.c_str(); }
@@ -93,7 +94,7 @@ extern "C" int lmc_user_kernel_build(const char* source, const char* type_name, 
   lmc_user_kernel k = {};
   k.kind = kind;
   k.tape = tape ? 1 : 0;
-  char name_expr[512];
+  char name_expr[512], probe_expr[512] = "";
   const char* header;
   if (kind == KIND_NUTS && (ndim + 1) / 2 <= 128) {
     if (!pick_warp_shape(ndim, chunk, &k.NP, &k.B)) return LMC_ERR_UNSUPPORTED;
@@ -105,6 +106,7 @@ extern "C" int lmc_user_kernel_build(const char* source, const char* type_name, 
     header = "lmc_sampler_warp.cuh";
     snprintf(name_expr, sizeof(name_expr), "lmc::sampler_warp_kernel<%s, %d, %d, 1, %d, %s>", type_name, k.NP, k.B, minb,
              k.tape ? "true" : "false");
+    snprintf(probe_expr, sizeof(probe_expr), "&lmc::warp_stage_probe<%s, %d, %d>", type_name, k.NP, k.B);
   } else {
     Shape s;
     if (!pick_shape(ndim, 0, &s)) return LMC_ERR_UNSUPPORTED;
@@ -115,7 +117,7 @@ extern "C" int lmc_user_kernel_build(const char* source, const char* type_name, 
     snprintf(name_expr, sizeof(name_expr), "lmc::sampler_kernel<%s, %d, %d, %d>", type_name, k.G, k.NP, kind);
   }
 
-  std::string cubin, lowered;
+  std::string cubin, lowered, lowered_probe;  // the .name file of a cached cubin: kernel name [newline probe name]
   const std::string cpath = cache_path ? cache_path : "";
   if (cpath.empty() || !read_file(cpath, &cubin) || !read_file(cpath + ".name", &lowered) || cubin.empty()) {
     if (!g_nvrtc.load()) {
@@ -127,6 +129,7 @@ extern "C" int lmc_user_kernel_build(const char* source, const char* type_name, 
     if (g_nvrtc.create(&prog, program.c_str(), "lmc_user_target.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
       return LMC_ERR_LAUNCH;
     g_nvrtc.add_name(prog, name_expr);
+    if (probe_expr[0]) g_nvrtc.add_name(prog, probe_expr);
     // same code generation as the library build (__graft_entry__.py): un-fused multiply-add, sm_100a
     // -default-device: unannotated declarations (the C prototypes of lmc_b200.h, helpers in the user source) are device code
     std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=false", "--generate-line-info",
@@ -152,6 +155,10 @@ extern "C" int lmc_user_kernel_build(const char* source, const char* type_name, 
       return LMC_ERR_LAUNCH;
     }
     lowered = low;
+    if (probe_expr[0]) {
+      const char* lowp = nullptr;
+      if (g_nvrtc.lowered(prog, probe_expr, &lowp) == NVRTC_SUCCESS && lowp) lowered += std::string("\n") + lowp;
+    }
     size_t cs = 0;
     g_nvrtc.cubin_size(prog, &cs);
     cubin.resize(cs);
@@ -162,8 +169,21 @@ extern "C" int lmc_user_kernel_build(const char* source, const char* type_name, 
       write_file_atomic(cpath + ".name", lowered);
     }
   }
+  const size_t nl = lowered.find('\n');
+  if (nl != std::string::npos) {
+    lowered_probe = lowered.substr(nl + 1);
+    lowered.resize(nl);
+  }
   LMC_CUDA(cudaLibraryLoadData(&k.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
   LMC_CUDA(cudaLibraryGetKernel(&k.kern, k.lib, lowered.c_str()));
+  k.stage_vecs = 0;
+  if (!lowered_probe.empty()) {
+    void* dptr = nullptr;
+    size_t bytes = 0;
+    LMC_CUDA(cudaLibraryGetGlobal(&dptr, &bytes, k.lib, lowered_probe.c_str()));
+    if (bytes != sizeof(int)) return LMC_ERR_LAUNCH;
+    LMC_CUDA(cudaMemcpy(&k.stage_vecs, dptr, sizeof(int), cudaMemcpyDeviceToHost));
+  }
   *out = new lmc_user_kernel(k);
   return LMC_OK;
 }
@@ -186,7 +206,8 @@ extern "C" int lmc_user_sample(lmc_user_kernel* k, const lmc_sampler_args* a, co
   if (k->warp) {
     int NP = 0, B = 0;
     if (!pick_warp_shape(a->ndim, k->B, &NP, &B) || NP != k->NP) return LMC_ERR_BADARG;  // built for another ndim
-#define LMC_X(n, bb, mb) if (k->NP == n && k->B == bb) return launch_warp_kernel<n, bb, 1>(kern, *a, target_bytes);
+#define LMC_X(n, bb, mb) \
+  if (k->NP == n && k->B == bb) return launch_warp_kernel<n, bb, 1>(kern, *a, target_bytes, k->stage_vecs);
     LMC_WARP_SHAPES(LMC_X)
 #undef LMC_X
     return LMC_ERR_UNSUPPORTED;

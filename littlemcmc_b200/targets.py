@@ -121,7 +121,7 @@ class CudaTarget:
 _ELEMENTWISE_TEMPLATE = """
 struct %(name)s {
   static constexpr int kPre = 0;
-  const double* params;  // [n_params][ld] rows, ld = ndim rounded up to even, padding 0
+  %(member)s
   template <int G, int NP>
   __device__ __forceinline__ void pre(int, int, const double2 (&)[NP], double (&)[2]) const {}
   template <int G, int NP>
@@ -162,6 +162,28 @@ struct %(name)s {
 """
 
 
+# One parameter vector: the chunked warp kernel may keep it in shared memory (csrc/lmc_device.cuh: StageTraits; it does
+# where the slot has a spare KB, i.e. 65..128 dimensions) -- the same element code reading the staged copy.
+_STAGE_TRAITS_TEMPLATE = """
+namespace lmc {
+template <>
+struct StageTraits< ::%(name)s> {
+  static constexpr int kVecs = 1;
+  using Staged = ::%(name)s_S;
+  template <int NP>
+  static __device__ __forceinline__ Staged make(const ::%(name)s& t, double2* s_lane, int lane, int ldh) {
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      const int j = lane + k * 32;
+      s_lane[k * 32] = j < ldh ? __ldg(reinterpret_cast<const double2*>(t.params) + j) : make_double2(0.0, 0.0);
+    }
+    return Staged{s_lane};
+  }
+};
+}  // namespace lmc
+"""
+
+
 class ElementwiseTarget(CudaTarget):
     """Separable density ``logp(q) = sum_i f(q_i; theta_i)`` from two C expressions: ``logp`` = f and ``grad`` = df/dq,
     written in terms of ``q`` and the names of ``params`` (a dict name -> array[ndim] or scalar); ``logp`` may also use
@@ -185,7 +207,15 @@ class ElementwiseTarget(CudaTarget):
         loads = "\n".join("      const double2 %s_2 = j < ldh ? __ldg(reinterpret_cast<const double2*>(params + %d * 2 * (size_t)ldh) + j)"
                           " : make_double2(0.0, 0.0);" % (n, i) for i, n in enumerate(names))
         bind = lambda c: "\n".join("          const double %s = %s_2.%s;" % (n, n, c) for n in names)  # noqa: E731
-        src = _ELEMENTWISE_TEMPLATE % dict(name=name, loads=loads, bind_x=bind("x"), bind_y=bind("y"), grad=grad, logp=logp)
+        member = "const double* params;  // [n_params][ld] rows, ld = ndim rounded up to even, padding 0"
+        src = _ELEMENTWISE_TEMPLATE % dict(name=name, member=member, loads=loads, bind_x=bind("x"), bind_y=bind("y"),
+                                           grad=grad, logp=logp)
+        if len(names) == 1:
+            src += _ELEMENTWISE_TEMPLATE % dict(
+                name=name + "_S", member="const double2* stage;  // this lane's [NP][32] pairs of the staged parameter",
+                loads="      const double2 %s_2 = stage[k * G];" % names[0], bind_x=bind("x"), bind_y=bind("y"), grad=grad,
+                logp=logp)
+            src += _STAGE_TRAITS_TEMPLATE % dict(name=name)
         env = {k: getattr(np, k) for k in ("exp", "log", "sqrt", "tanh", "sin", "cos", "log1p", "expm1", "fabs")}
 
         def numpy_fn(q):
