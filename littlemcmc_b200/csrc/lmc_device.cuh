@@ -236,6 +236,8 @@ __device__ __forceinline__ void group_barrier() {
 //   pre(...)        per-thread partials of those sums
 //   grad(...)       g from q (and the reduced pre-sums); returns this thread's partial of the logp sum
 //   finish(...)     logp from the reduced logp sum and the pre-sums
+// Optional: a specialisation of StageTraits (below) names per-dimension parameter vectors the chunked warp kernel may
+// copy to shared memory once per launch, and the type that evaluates the target from that copy.
 struct DiagGaussian {
   static constexpr int kPre = 0;
   const double2* tau;  // [ldh] pairs, padding = 0

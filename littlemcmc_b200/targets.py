@@ -103,7 +103,9 @@ class CudaTarget:
     (csrc/lmc_device.cuh): ``static constexpr int kPre``; ``pre<G,NP>(lane, D, q, out)`` partial sums the gradient needs
     (if any); ``grad<G,NP>(lane, D, ldh, q, g, pre)`` writes this thread's gradient pairs and returns its partial of the
     log-density sum; ``finish(sum, pre)`` the log density.  Its only data member is ``const double* params``; ``params``
-    is uploaded once.  The sampler kernel is compiled for sm_100a at first use (NVRTC) and cached on disk.
+    is uploaded once.  Optionally the source specialises ``lmc::StageTraits<T>`` (csrc/lmc_device.cuh) to have a
+    per-dimension parameter vector kept in shared memory by the chunked warp kernel (``ElementwiseTarget`` does so for a
+    single parameter); the host reads what the compiled kernel stages from the module, nothing to declare.  The sampler kernel is compiled for sm_100a at first use (NVRTC) and cached on disk.
     ``numpy_fn`` (optional) is the same density as a reference-style callable ``q[D] -> (logp, dlogp[D])``
     (base_hmc.py:34), so that the object also drives the reference / the per-step integrator API."""
 
