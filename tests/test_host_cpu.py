@@ -145,6 +145,63 @@ def test_elementwise_target_expressions_and_generated_source():
         lmc.targets.ElementwiseTarget(3, logp="q * g", grad="-q", params={"g": np.ones(3)})
 
 
+def test_scheduler_protocol_model():
+    """A model of the transition scheduler of the fused kernels (csrc/lmc_sampler.cuh: ticket / peek / take / push with the
+    consumed-slot handshake) under random interleavings, including pushers that stall between taking their ticket and
+    publishing the entry (the late store must not overwrite the entry one ring later): every (chain, transition)
+    runs exactly once, in order per chain, and every group terminates."""
+    import random
+
+    def run(n_chains, n_trans, n_groups, seed):
+        rnd = random.Random(seed)
+        total = n_chains * n_trans
+        ring = [(i + 1, i, 0) for i in range(n_chains)]      # (ticket + 1, chain, t); None = consumed
+        head, tail = 0, n_chains
+        last_t = [-1] * n_chains
+        state = [("idle",)] * n_groups
+        finished = [False] * n_groups
+        steps = 0
+        while not all(finished):
+            steps += 1
+            assert steps < 400 * total + 10000, "scheduler model does not terminate"
+            g = rnd.randrange(n_groups)
+            if finished[g]:
+                continue
+            st = state[g]
+            if st[0] == "idle":                               # sched_ticket
+                tk, head = head, head + 1
+                if tk >= total:
+                    finished[g] = True
+                else:
+                    state[g] = ("take", tk)
+            elif st[0] == "take":                             # sched_take: spin until the entry of this ticket is there
+                e = ring[st[1] % n_chains]
+                if e is not None and e[0] == st[1] + 1:
+                    ring[st[1] % n_chains] = None             # consumed
+                    state[g] = ("run", e[1], e[2])
+            elif st[0] == "run":                              # one transition; the chain's transitions stay ordered
+                _, c, t = st
+                assert last_t[c] == t - 1
+                last_t[c] = t
+                if t + 1 < n_trans:
+                    tk, tail = tail, tail + 1                 # push ticket taken ...
+                    state[g] = ("push", tk, c, t + 1)
+                else:
+                    state[g] = ("idle",)
+            else:                                             # ... entry published only into a consumed slot (CAS)
+                _, tk, c, t = st
+                if rnd.random() < 0.3:                        # the pusher stalls for a while
+                    continue
+                if ring[tk % n_chains] is None:
+                    ring[tk % n_chains] = (tk + 1, c, t)
+                    state[g] = ("idle",)
+        assert last_t == [n_trans - 1] * n_chains and tail == total
+
+    for n_chains, n_trans, n_groups in ((1, 9, 3), (2, 7, 5), (5, 6, 2), (7, 5, 7), (16, 4, 3)):
+        for seed in range(4):
+            run(n_chains, n_trans, n_groups, seed)
+
+
 def test_no_cpu_fallback():
     """Binding chains to a non-CUDA device must fail loudly."""
     from littlemcmc_b200 import _lib as L, engine
