@@ -78,3 +78,40 @@ def test_oracle_matches_the_live_reference_on_fresh_cases(idx):
             np.testing.assert_allclose(np.asarray(v, dtype="d"), stats_ref[k], rtol=1e-12, atol=1e-300, err_msg=k)
     size = stats.get("tree_size", stats.get("n_steps"))
     assert size is not None and float(np.sum(size)) > 0
+
+
+@pytest.mark.parametrize("pot", ["full", "fullinv", "fulladapt"])
+def test_dense_oracle_matches_the_live_reference_on_a_fresh_case(pot):
+    """Dense potentials (reference quadpotential.py:390-615) on a freshly drawn 6-dimensional correlated Gaussian."""
+    ref = _reference()
+    rs = np.random.RandomState(777 + len(pot))
+    n = 6
+    A = rs.normal(size=(n, n))
+    cov = A @ A.T / n + np.eye(n) * 0.5
+    prec = np.linalg.inv(cov)
+    case = dict(kind="nuts", target="dense_gaussian", ndim=n, prec=prec, draws=4, tune=16, start=rs.normal(size=n) * 0.2,
+                seeds=[int(s) for s in rs.randint(1, 2 ** 30, size=2)], pot=pot,
+                pot_matrix=(prec if pot == "fullinv" else np.eye(n) if pot == "fulladapt" else cov),
+                pot_mean=np.zeros(n), pot_weight=5.0, adaptation_window=7, adaptation_window_multiplier=2.0,
+                max_treedepth=6, early_max_treedepth=5)
+    f = gc.target_fn(case)()
+    traces, stats_all = [], []
+    for seed in case["seeds"]:
+        if pot == "full":
+            p = ref.QuadPotentialFull(np.array(case["pot_matrix"]), dtype="float64")
+        elif pot == "fullinv":
+            p = ref.QuadPotentialFullInv(np.array(case["pot_matrix"]), dtype="float64")
+        else:
+            p = ref.QuadPotentialFullAdapt(n, np.zeros(n), np.array(case["pot_matrix"]), case["pot_weight"],
+                                           adaptation_window=7, adaptation_window_multiplier=2.0, dtype="float64")
+        step = ref.NUTS(logp_dlogp_func=f, model_ndim=n, potential=p, **gc.sampler_kw(case))
+        trace, stats = ref.sample(f, n, draws=4, tune=16, step=step, chains=1, cores=1, start=np.array(case["start"]),
+                                  progressbar=False, random_seed=[int(seed)], discard_tuned_samples=False)
+        traces.append(trace[0])
+        stats_all.append({k: np.asarray(v[0, :, 0], dtype="d") for k, v in stats.items()})
+    trace_ref = np.stack(traces)
+    trace, stats, _ = gc.run_oracle_dense(case)
+    np.testing.assert_allclose(trace, trace_ref, rtol=1e-10, atol=1e-300)   # Cholesky / solves: LAPACK vs LAPACK
+    for k in gc.EXACT_STATS:
+        if k in stats:
+            assert np.array_equal(np.asarray(stats[k], dtype="d"), np.stack([s[k] for s in stats_all])), k
